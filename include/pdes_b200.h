@@ -1,0 +1,126 @@
+/* pdes_b200.h -- C ABI of the B200-native U-FNO / FNO spectral block.
+ *
+ * This is the drop-in boundary for the hot path of yoeripoels/neural-pde-surrogates.  The reference has
+ * no FFI of its own (it is pure PyTorch); each entry point below cites the reference lines (relative to
+ * /root/reference/src) whose work it replaces.  The reference-side binding is a `torch.autograd.Function`
+ * that passes `tensor.data_ptr()` and `torch.cuda.current_stream().cuda_stream`.
+ *
+ * Conventions
+ *   - all buffers are DEVICE pointers owned by the caller (PyTorch); the library never allocates,
+ *     frees or synchronises, so every call is CUDA-graph capturable;
+ *   - float32 everywhere; complex values are interleaved (re, im) pairs == torch.complex64 memory;
+ *   - activations are NCHW contiguous; `stream` is a cudaStream_t passed as void*;
+ *   - return value 0 = ok, otherwise a PDES_ERR_* code; `pdes_last_error()` gives the message
+ *     (the Python binding raises RuntimeError/ValueError from it);
+ *   - retained modes: rows kx in [0,m1) U [H-m1,H) (index k in [0,2*m1)), columns ky in [0,m2);
+ *     "MM" = m1*m2; spectra are stored [B][C][2*m1][m2] complex (mode index fastest), which is also the
+ *     mode order of the reference parameters weights1/weights2 [Cin][Cout][m1][m2] (proc_fno.py:240-243).
+ */
+#ifndef PDES_B200_H_
+#define PDES_B200_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PDES_OK 0
+#define PDES_ERR_ARG 1         /* null pointer / non-positive size / modes out of range (proc_fno.py:135-139 asserts) */
+#define PDES_ERR_UNSUPPORTED 2 /* shape needs more shared memory than one sm_100a CTA has */
+#define PDES_ERR_LAUNCH 3      /* cudaGetLastError() != cudaSuccess after a launch */
+
+#define PDES_ACT_NONE 0
+#define PDES_ACT_GELU 1        /* exact erf GELU == nn.GELU() default (proc_ufno.py:44,118; proc_fno.py:94,153) */
+
+int pdes_version(void);
+const char* pdes_last_error(void);
+/* 1 when built by nvcc for sm_100a, 0 for the CPU emulation build used by the CPU tests. */
+int pdes_is_cuda_build(void);
+
+/* ---- twiddle tables (host side, float64 math rounded once to float32) -------------------------------
+ * The caller fills a host buffer once per (H, W, m1, m2), uploads it, and passes the device copy as
+ * `tables` to the kernels below. */
+size_t pdes_tables_floats(int H, int W, int m1, int m2);
+int pdes_tables_fill(int H, int W, int m1, int m2, float* host_buf);
+
+/* ---- K1: pruned forward DFT -------------------------------------------------------------------------
+ * Replaces torch.fft.rfft2 + the two mode slices (proc_fno.py:261,267,269) and, with herm_scale=1, the
+ * FftC2RBackward of irfft2 (GO = c_l/(HW) * DFT(g)).  The input is the channel concatenation of x0
+ * [B,C0,H,W] and x1 [B,C1,H,W] (x1 may be NULL with C1=0): this removes torch.cat (proc_ufno.py:111).
+ * X: [B][C0+C1][2*m1][m2] complex. */
+int pdes_dft_fwd(const float* x0, int C0, const float* x1, int C1, int B, int H, int W, int m1, int m2,
+                 const float* tables, int herm_scale, float* X, void* stream);
+
+/* ---- K2: per-mode complex channel mixing ------------------------------------------------------------
+ * Replaces compl_mul2d = einsum("bixy,ioxy->boxy") x2 (proc_fno.py:253-255,266-269) reading weights1 /
+ * weights2 in their native parameter layout.  Output is `nsplit` partial sums P[nsplit][B][Cout][2MM]
+ * (split over the reduction channel; the consumer K3a adds them, so the result is deterministic).
+ * Rows of the first block that the reference overwrites when 2*m1 > H are written as zero. */
+int pdes_mix_suggest_splits(int B, int Cred, int Cout, int m1, int m2);
+int pdes_mix_fwd(const float* X, const float* w1, const float* w2, float* P, int nsplit,
+                 int B, int Cin, int Cout, int H, int m1, int m2, void* stream);
+/* adjoint w.r.t. X: GX[b,i,m] = sum_o GO[b,o,m] * conj(W[i,o,m]) for i < Cgrad (<= Cin).
+ * P: [nsplit][B][Cgrad][2MM] partial sums. (BmmBackward of proc_fno.py:255) */
+int pdes_mix_dx(const float* GO, const float* w1, const float* w2, float* P, int nsplit,
+                int B, int Cin, int Cout, int Cgrad, int H, int m1, int m2, void* stream);
+/* adjoint w.r.t. the weights, written in the parameter layout: gw1/gw2 [Cin][Cout][m1][m2] complex. */
+int pdes_mix_dw(const float* X, const float* GO, float* gw1, float* gw2,
+                int B, int Cin, int Cout, int H, int m1, int m2, void* stream);
+
+/* ---- K3a: inverse DFT along H -----------------------------------------------------------------------
+ * Z[b][h][j][c] (c fastest, j = 2*l + {re,im}) = sum_k e^{+2 pi i kx_k h/H} * sum_s P[s][b][c][k][l].
+ * First half of torch.fft.irfft2 (proc_fno.py:287), without ever building the zero-padded spectrum
+ * (proc_fno.py:265). */
+int pdes_inv_h(const float* P, int nsplit, int B, int C, int H, int m1, int m2, const float* tables,
+               float* Z, void* stream);
+
+/* ---- K3b: inverse DFT along W fused with the 1x1 conv, bias, residual and activation ------------------
+ *   pre[b,o,h,w] = sum_j Z[b,h,j,o] * T[j,w]  +  sum_i At[i,o] * xin[b,i,h,w]  + bias[o] + res[b,o,h,w]
+ *   out = act(pre)
+ * Replaces the second half of irfft2 (proc_fno.py:287), self.w(x) (proc_fno.py:143), x1 + x2 (:146),
+ * h_fno + h_unet and the GELU (proc_ufno.py:118 / proc_fno.py:153-154).  At is the 1x1 weight stored
+ * [K][lda] with the output channel contiguous (forward: transpose of w.weight; backward dX: w.weight
+ * itself).  Z / At / bias / res / pre may each be NULL (term skipped).  `backward_scale` selects
+ * T with s_l = 1 (adjoint of K1) instead of c_l/(HW).  M = output channels, K = C0 + C1 input channels. */
+int pdes_inv_w_gemm(const float* Z, const float* At, int lda, const float* x0, int C0, const float* x1, int C1,
+                    const float* bias, const float* res, const float* tables, int backward_scale,
+                    float* out, float* pre, int B, int M, int H, int W, int m1, int m2, int act, void* stream);
+
+/* ---- pointwise / small helpers ------------------------------------------------------------------------
+ * g_pre = g_out * act'(pre)  (GeluBackward of proc_ufno.py:118) */
+int pdes_act_bwd(const float* g_out, const float* pre, float* g_pre, size_t n, int act, void* stream);
+/* out[k][m] = in[m][k]  (w.weight [Cout][Cin] -> At [Cin][Cout]) */
+int pdes_transpose(const float* in, float* out, int M, int K, void* stream);
+/* 1x1-conv weight and bias gradients (ConvolutionBackward of proc_fno.py:143):
+ *   dW[o][i] = sum_{b,p} g[b,o,p] * xin[b,i,p],  dbias[o] = sum_{b,p} g[b,o,p]
+ * ws needs pdes_wgrad_workspace_floats() floats. */
+size_t pdes_wgrad_workspace_floats(int B, int M, int K, int HW);
+int pdes_wgrad(const float* g, const float* x0, int C0, const float* x1, int C1, float* dW, float* dbias,
+               float* ws, int B, int M, int HW, void* stream);
+
+/* ---- fused chains (what the nn.Module binding calls) ----------------------------------------------------
+ * One FNO_Layer / U-FNO block tail, forward:  K1 -> K2 -> K3a -> K3b.
+ *   h [B,C0,H,W], vb [B,C1,H,W] or NULL, w1/w2 complex [Cin][Cout][m1][m2], wct [Cin][Cout] (NULL = no 1x1),
+ *   bias [Cout] or NULL, res [B,Cout,H,W] or NULL (the U-Net branch), out [B,Cout,H,W],
+ *   pre (NULL unless the backward will need it), Xsave [B][Cin][2MM] complex (kept for the backward),
+ *   ws: pdes_block_fwd_workspace_floats() floats. */
+size_t pdes_block_fwd_workspace_floats(int B, int Cin, int Cout, int H, int W, int m1, int m2);
+int pdes_block_forward(const float* h, int C0, const float* vb, int C1, const float* w1, const float* w2,
+                       const float* wct, const float* bias, const float* res, const float* tables,
+                       float* Xsave, float* ws, float* out, float* pre,
+                       int B, int Cout, int H, int W, int m1, int m2, int act, void* stream);
+/* backward of the same block.  Inputs: g_out, pre (if act != none), h, vb, Xsave, w1, w2, wc [Cout][Cin].
+ * Outputs: g_pre [B,Cout,H,W] (also the gradient of `res`), dh [B,C0,H,W], gw1/gw2 (parameter layout),
+ * dwc [Cout][Cin] and dbias [Cout] (both may be NULL when there is no 1x1 conv). */
+size_t pdes_block_bwd_workspace_floats(int B, int C0, int C1, int Cout, int H, int W, int m1, int m2);
+int pdes_block_backward(const float* g_out, const float* pre, const float* h, int C0, const float* vb, int C1,
+                        const float* Xsave, const float* w1, const float* w2, const float* wc,
+                        const float* tables, float* ws, float* g_pre, float* dh, float* gw1, float* gw2,
+                        float* dwc, float* dbias,
+                        int B, int Cout, int H, int W, int m1, int m2, int act, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PDES_B200_H_ */

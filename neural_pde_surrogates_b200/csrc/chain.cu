@@ -1,0 +1,104 @@
+// Fused launch chains for one FNO_Layer / U-FNO block tail (forward and backward).
+// These are the two entry points the nn.Module binding calls; each enqueues a fixed sequence of kernels on
+// the caller's stream (no allocation, no synchronisation => CUDA-graph capturable).
+#include "pdes_common.cuh"
+
+namespace pdes {
+namespace {
+
+struct FwdWs { size_t P, Z, total; int nsplit; };
+FwdWs fwd_ws(int B, int Cin, int Cout, int H, int W, int m1, int m2) {
+  (void)W;
+  FwdWs w;
+  w.nsplit = pdes_mix_suggest_splits(B, Cin, Cout, m1, m2);
+  const size_t M2 = (size_t)2 * m1 * m2;
+  w.P = 0;
+  w.Z = w.P + round4((size_t)w.nsplit * B * Cout * M2 * 2);
+  w.total = w.Z + round4((size_t)B * H * 2 * m2 * Cout);
+  return w;
+}
+
+struct BwdWs { size_t GO, PX, Zg, WG, total; int nsplit; };
+BwdWs bwd_ws(int B, int Cin, int C0, int Cout, int H, int W, int m1, int m2, bool has_conv) {
+  BwdWs w;
+  w.nsplit = pdes_mix_suggest_splits(B, Cout, C0, m1, m2);
+  const size_t M2 = (size_t)2 * m1 * m2;
+  w.GO = 0;
+  w.PX = w.GO + round4((size_t)B * Cout * M2 * 2);
+  w.Zg = w.PX + round4((size_t)w.nsplit * B * C0 * M2 * 2);
+  w.WG = w.Zg + round4((size_t)B * H * 2 * m2 * C0);
+  w.total = w.WG + (has_conv ? round4(pdes_wgrad_workspace_floats(B, Cout, Cin, H * W)) : 0);
+  return w;
+}
+
+}  // namespace
+}  // namespace pdes
+
+extern "C" {
+
+size_t pdes_block_fwd_workspace_floats(int B, int Cin, int Cout, int H, int W, int m1, int m2) {
+  if (B <= 0 || Cin <= 0 || Cout <= 0 || H <= 0 || W <= 0 || m1 <= 0 || m2 <= 0) return 0;
+  return pdes::fwd_ws(B, Cin, Cout, H, W, m1, m2).total;
+}
+
+int pdes_block_forward(const float* h, int C0, const float* vb, int C1, const float* w1, const float* w2,
+                       const float* wct, const float* bias, const float* res, const float* tables, float* Xsave,
+                       float* ws, float* out, float* pre, int B, int Cout, int H, int W, int m1, int m2, int act,
+                       void* stream) {
+  using namespace pdes;
+  PDES_REQUIRE(h && w1 && w2 && tables && Xsave && ws && out, PDES_ERR_ARG, "pdes_block_forward: null pointer");
+  const int Cin = C0 + C1;
+  const FwdWs w = fwd_ws(B, Cin, Cout, H, W, m1, m2);
+  float* P = ws + w.P;
+  float* Z = ws + w.Z;
+  if (int e = pdes_dft_fwd(h, C0, vb, C1, B, H, W, m1, m2, tables, 0, Xsave, stream)) return e;
+  if (int e = pdes_mix_fwd(Xsave, w1, w2, P, w.nsplit, B, Cin, Cout, H, m1, m2, stream)) return e;
+  if (int e = pdes_inv_h(P, w.nsplit, B, Cout, H, m1, m2, tables, Z, stream)) return e;
+  return pdes_inv_w_gemm(Z, wct, Cout, h, C0, vb, C1, bias, res, tables, 0, out, pre, B, Cout, H, W, m1, m2, act,
+                         stream);
+}
+
+size_t pdes_block_bwd_workspace_floats(int B, int C0, int C1, int Cout, int H, int W, int m1, int m2) {
+  if (B <= 0 || C0 <= 0 || C1 < 0 || Cout <= 0 || H <= 0 || W <= 0 || m1 <= 0 || m2 <= 0) return 0;
+  return pdes::bwd_ws(B, C0 + C1, C0, Cout, H, W, m1, m2, true).total;
+}
+
+int pdes_block_backward(const float* g_out, const float* pre, const float* h, int C0, const float* vb, int C1,
+                        const float* Xsave, const float* w1, const float* w2, const float* wc, const float* tables,
+                        float* ws, float* g_pre, float* dh, float* gw1, float* gw2, float* dwc, float* dbias, int B,
+                        int Cout, int H, int W, int m1, int m2, int act, void* stream) {
+  using namespace pdes;
+  PDES_REQUIRE(g_out && h && Xsave && w1 && w2 && tables && ws && dh && gw1 && gw2, PDES_ERR_ARG,
+               "pdes_block_backward: null pointer");
+  PDES_REQUIRE(act == PDES_ACT_NONE || (pre != nullptr && g_pre != nullptr), PDES_ERR_ARG,
+               "pdes_block_backward: activation backward needs pre and g_pre");
+  const int Cin = C0 + C1;
+  const bool has_conv = wc != nullptr;
+  const BwdWs w = bwd_ws(B, Cin, C0, Cout, H, W, m1, m2, has_conv);
+  float* GO = ws + w.GO;
+  float* PX = ws + w.PX;
+  float* Zg = ws + w.Zg;
+  float* WG = ws + w.WG;
+  const float* gp = g_out;
+  if (act != PDES_ACT_NONE) {
+    if (int e = pdes_act_bwd(g_out, pre, g_pre, (size_t)B * Cout * H * W, act, stream)) return e;
+    gp = g_pre;
+  }
+  // GO = c_l/(HW) * DFT(g_pre)                     (adjoint of K3)
+  if (int e = pdes_dft_fwd(gp, Cout, nullptr, 0, B, H, W, m1, m2, tables, 1, GO, stream)) return e;
+  // weight gradients in the parameter layout       (adjoint of K2 w.r.t. W)
+  if (int e = pdes_mix_dw(Xsave, GO, gw1, gw2, B, Cin, Cout, H, m1, m2, stream)) return e;
+  // GX for the C0 channels that need a gradient    (adjoint of K2 w.r.t. X)
+  if (int e = pdes_mix_dx(GO, w1, w2, PX, w.nsplit, B, Cin, Cout, C0, H, m1, m2, stream)) return e;
+  // dh = Re(pruned inverse of GX, unit weights) + wc^T g_pre      (adjoint of K1 fused with the 1x1 dX)
+  if (int e = pdes_inv_h(PX, w.nsplit, B, C0, H, m1, m2, tables, Zg, stream)) return e;
+  if (int e = pdes_inv_w_gemm(Zg, wc, Cin, has_conv ? gp : nullptr, Cout, nullptr, 0, nullptr, nullptr, tables, 1, dh,
+                              nullptr, B, C0, H, W, m1, m2, PDES_ACT_NONE, stream))
+    return e;
+  if (has_conv && (dwc != nullptr || dbias != nullptr)) {
+    if (int e = pdes_wgrad(gp, h, C0, vb, C1, dwc, dbias, WG, B, Cout, H * W, stream)) return e;
+  }
+  return PDES_OK;
+}
+
+}  // extern "C"

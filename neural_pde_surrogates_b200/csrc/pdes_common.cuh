@@ -1,0 +1,78 @@
+// Shared helpers for the sm_100a kernels of the U-FNO spectral block.
+#pragma once
+
+#include "pdes_emu.h"
+#ifndef PDES_CPU_EMU
+#include <cuda_runtime.h>
+#define PDES_DYN_SMEM(T, name)                                      \
+  extern __shared__ __align__(16) unsigned char _pdes_dyn_smem[];   \
+  T* name = reinterpret_cast<T*>(_pdes_dyn_smem)
+#define PDES_LAUNCH(kernel, grid, block, smem, stream, ...) \
+  kernel<<<(grid), (block), (smem), (cudaStream_t)(stream)>>>(__VA_ARGS__)
+#define PDES_SET_SMEM(kernel, bytes) \
+  cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))
+#endif
+
+#include <cstddef>
+#include <cstdint>
+#include <cstdio>
+
+#include "../../include/pdes_b200.h"
+
+namespace pdes {
+
+constexpr int kMaxDynSmem = 200 * 1024;   // leave headroom below the 227 KB sm_100a CTA limit
+
+// ---- error plumbing ---------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+int check_launch(const char* what);
+
+#define PDES_REQUIRE(cond, code, ...)         \
+  do {                                        \
+    if (!(cond)) {                            \
+      pdes::set_error(__VA_ARGS__);           \
+      return (code);                          \
+    }                                         \
+  } while (0)
+
+// ---- twiddle table blob layout (floats) ---------------------------------------------------------------
+// twh    [H][2]        (cos, sin)(2 pi j / H)
+// twa    [W][NC4]      K1 stage A: col 2l -> cos(2 pi l w / W), col 2l+1 -> -sin(2 pi l w / W), zero padded
+// tinv_f [2*m2][W]     K3b forward:  row 2l -> s_l cos(2 pi l w / W), row 2l+1 -> -s_l sin(..), s_l = c_l/(HW)
+// tinv_b [2*m2][W]     K3b backward: same with s_l = 1
+// herm   [m2]          s_l
+struct TableLayout {
+  int nc4;
+  size_t twh, twa, tinv_f, tinv_b, herm, total;
+};
+__host__ __device__ inline size_t round4(size_t n) { return (n + 3) & ~size_t(3); }
+__host__ __device__ inline TableLayout table_layout(int H, int W, int m1, int m2) {
+  (void)m1;
+  TableLayout t;
+  t.nc4 = (int)round4((size_t)2 * m2);
+  t.twh = 0;
+  t.twa = t.twh + round4((size_t)2 * H);
+  t.tinv_f = t.twa + (size_t)W * t.nc4;
+  t.tinv_b = t.tinv_f + round4((size_t)2 * m2 * W);
+  t.herm = t.tinv_b + round4((size_t)2 * m2 * W);
+  t.total = t.herm + round4((size_t)m2);
+  return t;
+}
+
+// retained row k -> frequency index (proc_fno.py:266-269)
+__host__ __device__ inline int kx_of(int k, int m1, int H) { return k < m1 ? k : H - 2 * m1 + k; }
+// first-block rows overwritten by the second block when 2*m1 > H
+__host__ __device__ inline bool row_dead(int k, int m1, int H) { return k < m1 && k >= H - m1; }
+
+__host__ __device__ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+__host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// exact GELU and its derivative (nn.GELU() default, approximate='none')
+__device__ __forceinline__ float gelu_f(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f)); }
+__device__ __forceinline__ float gelu_grad_f(float v) {
+  const float cdf = 0.5f * (1.0f + erff(v * 0.70710678118654752440f));
+  const float pdf = 0.39894228040143267794f * expf(-0.5f * v * v);
+  return cdf + v * pdf;
+}
+
+}  // namespace pdes

@@ -1,0 +1,152 @@
+// K1: pruned forward DFT  x[B,C,H,W] (real) -> X[B,C,2*m1,m2] (complex), only the retained modes.
+//
+// Replaces torch.fft.rfft2 + mode slicing (reference proc_fno.py:261,267,269).  One CTA per image (b,c):
+//   stage A  Y[h,l]  = sum_w x[h,w] e^{-2 pi i l w/W}         rows staged in shared memory, 4x4 register tiles
+//   stage B  X[k,l]  = sum_h Y[h,l] e^{-2 pi i kx_k h/H}      Y kept in shared memory
+// The image is read from HBM exactly once (coalesced 128-bit loads); everything else stays on chip.
+// Generic in (H, W, m1, m2): rows are processed in chunks of R so that large grids still fit.
+#include "pdes_common.cuh"
+
+namespace pdes {
+namespace {
+
+constexpr int kK1Threads = 128;
+
+__global__ void __launch_bounds__(kK1Threads)
+k_dft_fwd(const float* __restrict__ x0, int C0, const float* __restrict__ x1, int C1, int H, int W, int m1, int m2,
+          int nc4, int R, int xs_stride, const float* __restrict__ twa_g, const float* __restrict__ twh_g,
+          const float* __restrict__ lscale, float* __restrict__ X) {
+  PDES_DYN_SMEM(float, smem);
+  float* xs = smem;                                     // [R][xs_stride]
+  float* twa = xs + round4((size_t)R * xs_stride);      // [W][nc4]
+  float* ys = twa + (size_t)W * nc4;                    // [H][2*m2]
+  float* twh = ys + round4((size_t)H * 2 * m2);         // [H][2]
+
+  const int C = C0 + C1;
+  const int img = blockIdx.x;
+  const int b = img / C, c = img % C;
+  const float* src = (c < C0) ? x0 + ((size_t)b * C0 + c) * H * W : x1 + ((size_t)b * C1 + (c - C0)) * H * W;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int J = 2 * m2;
+
+  for (int i = tid; i < W * nc4; i += nt) twa[i] = __ldg(twa_g + i);
+  for (int i = tid; i < 2 * H; i += nt) twh[i] = __ldg(twh_g + i);
+
+  const bool vec = (W % 4 == 0) && aligned16(src);
+  const int ncg = nc4 / 4;
+
+  for (int h0 = 0; h0 < H; h0 += R) {
+    const int rc = (H - h0 < R) ? (H - h0) : R;
+    __syncthreads();   // previous chunk fully consumed; tables visible
+    if (vec) {
+      const float4* s4 = reinterpret_cast<const float4*>(src + (size_t)h0 * W);
+      const int nq = rc * W / 4;
+      for (int q = tid; q < nq; q += nt) {
+        const float4 v = __ldg(s4 + q);
+        const int e = q * 4;
+        float* d = xs + (e / W) * xs_stride + (e % W);
+        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+      }
+    } else {
+      const float* s1 = src + (size_t)h0 * W;
+      for (int e = tid; e < rc * W; e += nt) xs[(e / W) * xs_stride + (e % W)] = __ldg(s1 + e);
+    }
+    __syncthreads();
+
+    // ---- stage A: 4 rows x 4 table columns per item
+    const int nrg = ceil_div(rc, 4);
+    for (int item = tid; item < nrg * ncg; item += nt) {
+      const int rg = item / ncg, cg = item % ncg;
+      const int r0 = rg * 4;
+      const float* xr[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int rr = (r0 + j < rc) ? (r0 + j) : (rc - 1);
+        xr[j] = xs + rr * xs_stride;
+      }
+      float acc[4][4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[j][e] = 0.0f;
+      const float* tw = twa + cg * 4;
+#pragma unroll 4
+      for (int w = 0; w < W; ++w) {
+        const float4 t = *reinterpret_cast<const float4*>(tw + (size_t)w * nc4);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float xv = xr[j][w];
+          acc[j][0] = fmaf(xv, t.x, acc[j][0]);
+          acc[j][1] = fmaf(xv, t.y, acc[j][1]);
+          acc[j][2] = fmaf(xv, t.z, acc[j][2]);
+          acc[j][3] = fmaf(xv, t.w, acc[j][3]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (r0 + j < rc) {
+          float* y = ys + (size_t)(h0 + r0 + j) * J + cg * 4;
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if (cg * 4 + e < J) y[e] = acc[j][e];
+        }
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- stage B: one retained mode (k,l) per work item
+  const int nout = 2 * m1 * m2;
+  for (int n = tid; n < nout; n += nt) {
+    const int k = n / m2, l = n % m2;
+    const int kx = kx_of(k, m1, H);
+    float ar = 0.0f, ai = 0.0f;
+    int j = 0;
+    const float* yl = ys + 2 * l;
+    for (int h = 0; h < H; ++h) {
+      const float yr = yl[(size_t)h * J], yi = yl[(size_t)h * J + 1];
+      const float cs = twh[2 * j], sn = twh[2 * j + 1];
+      ar = fmaf(yr, cs, fmaf(yi, sn, ar));      // (yr + i yi)(cs - i sn)
+      ai = fmaf(yi, cs, fmaf(-yr, sn, ai));
+      j += kx;
+      if (j >= H) j -= H;
+    }
+    if (lscale != nullptr) {
+      const float sc = __ldg(lscale + l);
+      ar *= sc; ai *= sc;
+    }
+    float* o = X + ((size_t)img * nout + n) * 2;
+    o[0] = ar; o[1] = ai;
+  }
+}
+
+}  // namespace
+}  // namespace pdes
+
+extern "C" int pdes_dft_fwd(const float* x0, int C0, const float* x1, int C1, int B, int H, int W, int m1, int m2,
+                            const float* tables, int herm_scale, float* X, void* stream) {
+  using namespace pdes;
+  PDES_REQUIRE(x0 != nullptr && tables != nullptr && X != nullptr, PDES_ERR_ARG, "pdes_dft_fwd: null pointer");
+  PDES_REQUIRE(B > 0 && C0 > 0 && C1 >= 0 && H > 0 && W > 0, PDES_ERR_ARG, "pdes_dft_fwd: non-positive size");
+  PDES_REQUIRE((C1 == 0) == (x1 == nullptr), PDES_ERR_ARG, "pdes_dft_fwd: x1/C1 mismatch");
+  PDES_REQUIRE(m1 > 0 && m2 > 0 && m1 <= H && m2 <= W / 2 + 1, PDES_ERR_ARG,
+               "modes (%d,%d) exceed the grid (%d,%d): need m1 <= H and m2 <= W/2+1", m1, m2, H, W);
+  const TableLayout t = table_layout(H, W, m1, m2);
+  const int xs_stride = (W % 2 == 0) ? W + 1 : W;
+  const size_t fixed = (size_t)W * t.nc4 + round4((size_t)H * 2 * m2) + round4((size_t)2 * H);
+  auto bytes_for = [&](int R) { return (round4((size_t)R * xs_stride) + fixed) * sizeof(float); };
+  int R = H;
+  if (bytes_for(R) > 48 * 1024) {
+    while (R > 4 && bytes_for(R) > 96 * 1024) R = (R > 8) ? ((R / 2 + 3) & ~3) : 4;
+    while (R > 4 && bytes_for(R) > (size_t)kMaxDynSmem) R = (R > 8) ? ((R / 2 + 3) & ~3) : 4;
+  }
+  PDES_REQUIRE(bytes_for(R) <= (size_t)kMaxDynSmem, PDES_ERR_UNSUPPORTED,
+               "pdes_dft_fwd: H=%d W=%d m2=%d needs %zu B of shared memory", H, W, m2, bytes_for(R));
+  const size_t smem = bytes_for(R);
+  auto kfn = k_dft_fwd;
+  if (smem > 48 * 1024) PDES_SET_SMEM(kfn, smem);
+  const float* lscale = herm_scale ? tables + t.herm : nullptr;
+  PDES_LAUNCH(kfn, dim3((unsigned)(B * (C0 + C1))), dim3(kK1Threads), smem, stream, x0, C0, x1, C1, H, W, m1, m2,
+              t.nc4, R, xs_stride, tables + t.twa, tables + t.twh, lscale, X);
+  return check_launch("pdes_dft_fwd");
+}

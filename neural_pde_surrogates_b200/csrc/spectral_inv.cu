@@ -1,0 +1,349 @@
+// K3: pruned inverse DFT fused with the 1x1 conv, bias, residual (U-Net branch) and GELU.
+//
+//   K3a  Z[b][h][j][c]   = sum_k e^{+2 pi i kx_k h/H} O[b][c][k][l]          (j = 2l + {re,im}, c fastest)
+//   K3b  pre[b][o][h][w] = sum_j Z[b][h][j][o] T[j][w] + sum_i At[i][o] xin[b][i][h][w] + bias[o] + res[b][o][h][w]
+//        out             = act(pre)
+// Replaces zero-padding + torch.fft.irfft2 (reference proc_fno.py:265-269,287), self.w(x) (:143), x1 + x2 (:146),
+// h_fno + h_unet and the activation (proc_ufno.py:118 / proc_fno.py:153-154): one pass over the activations,
+// one vectorised write.  In K3b the W-axis inverse DFT is simply 2*m2 extra reduction steps of the channel GEMM
+// whose "weight" operand is the row's Z vector, so the spectral term never exists as a tensor in HBM.
+#include "pdes_common.cuh"
+
+namespace pdes {
+namespace {
+
+// ------------------------------------------------------------------------------------------------- K3a
+constexpr int kInvHRows = 8;      // rows of h per CTA (one per warp)
+constexpr int kInvHLd = 33;       // padded channel stride (in float2) of the shared tile
+
+__global__ void __launch_bounds__(32 * kInvHRows)
+k_inv_h(const float2* __restrict__ P, int nsplit, int B, int C, int H, int m1, int m2, int LC,
+        const float* __restrict__ twh_g, float* __restrict__ Z) {
+  PDES_DYN_SMEM(float2, smem2);
+  const int K = 2 * m1;
+  float2* Os = smem2;                               // [K][LC][kInvHLd]
+  float2* twh = Os + (size_t)K * LC * kInvHLd;      // [H]
+  const int lane = threadIdx.x, wy = threadIdx.y;
+  const int tid = wy * 32 + lane, nt = 32 * kInvHRows;
+  const int c0 = blockIdx.x * 32;
+  const int h = blockIdx.y * kInvHRows + wy;
+  const int b = blockIdx.z;
+  const int J = 2 * m2;
+
+  for (int i = tid; i < H; i += nt) twh[i] = make_float2(__ldg(twh_g + 2 * i), __ldg(twh_g + 2 * i + 1));
+
+  for (int l0 = 0; l0 < m2; l0 += LC) {
+    const int lcn = (m2 - l0 < LC) ? (m2 - l0) : LC;
+    __syncthreads();
+    const int total = 32 * K * lcn;
+    for (int idx = tid; idx < total; idx += nt) {
+      const int lc = idx % lcn;
+      const int k = (idx / lcn) % K;
+      const int oo = idx / (lcn * K);
+      const int c = c0 + oo;
+      float2 v = make_float2(0.f, 0.f);
+      if (c < C) {
+        for (int s = 0; s < nsplit; ++s) {
+          const float2 pv = __ldg(P + ((((size_t)s * B + b) * C + c) * K + k) * m2 + l0 + lc);
+          v.x += pv.x; v.y += pv.y;
+        }
+      }
+      Os[((size_t)k * LC + lc) * kInvHLd + oo] = v;
+    }
+    __syncthreads();
+    if (h < H && c0 + lane < C) {
+      for (int lc = 0; lc < lcn; ++lc) {
+        float ar = 0.f, ai = 0.f;
+        for (int k = 0; k < K; ++k) {
+          const int kx = kx_of(k, m1, H);
+          const int j = (int)(((long)kx * h) % H);
+          const float2 t = twh[j];                                  // e^{+i theta} = (cos, sin)
+          const float2 o = Os[((size_t)k * LC + lc) * kInvHLd + lane];
+          ar = fmaf(o.x, t.x, fmaf(-o.y, t.y, ar));
+          ai = fmaf(o.x, t.y, fmaf(o.y, t.x, ai));
+        }
+        float* z = Z + (((size_t)b * H + h) * J + 2 * (l0 + lc)) * C + c0 + lane;
+        z[0] = ar;
+        z[C] = ai;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------- K3b
+constexpr int kBM = 64, kBN = 128, kBK = 16, kGemmThreads = 128;
+
+struct InvWParams {
+  const float* Z;      // [B][H][2*m2][M] or null
+  const float* At;     // [K][lda] or null
+  int lda;
+  const float* x0; int C0;
+  const float* x1; int C1;
+  const float* bias;   // [M] or null
+  const float* res;    // [B][M][HW] or null
+  const float* T;      // [2*m2][W]
+  float* out;          // [B][M][HW]
+  float* pre;          // [B][M][HW] or null
+  int M, H, W, m2, act;
+};
+
+__device__ __forceinline__ float4 load4g(const float* p, int nvalid, bool vec) {
+  if (nvalid >= 4 && vec) return __ldg(reinterpret_cast<const float4*>(p));
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (nvalid > 0) v.x = __ldg(p);
+  if (nvalid > 1) v.y = __ldg(p + 1);
+  if (nvalid > 2) v.z = __ldg(p + 2);
+  if (nvalid > 3) v.w = __ldg(p + 3);
+  return v;
+}
+
+__device__ __forceinline__ void store4g(float* p, float4 v, int nvalid, bool vec) {
+  if (nvalid >= 4 && vec) { *reinterpret_cast<float4*>(p) = v; return; }
+  if (nvalid > 0) p[0] = v.x;
+  if (nvalid > 1) p[1] = v.y;
+  if (nvalid > 2) p[2] = v.z;
+  if (nvalid > 3) p[3] = v.w;
+}
+
+__device__ __forceinline__ int clamp04(int n) { return n < 0 ? 0 : (n > 4 ? 4 : n); }
+
+template <bool ROWVEC>
+__global__ void __launch_bounds__(kGemmThreads)
+k_inv_w_gemm(InvWParams p) {
+  __align__(16) __shared__ float As[2][kBK][kBM];
+  __align__(16) __shared__ float Bs[2][kBK][kBN];
+
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int p0 = blockIdx.x * kBN, m0 = blockIdx.y * kBM, b = blockIdx.z;
+  const int HW = p.H * p.W, W = p.W, M = p.M;
+  const int K = (p.At != nullptr) ? (p.C0 + p.C1) : 0;
+  const int oa[2] = {m0 + ty * 4, m0 + 32 + ty * 4};
+  const int pg[2] = {p0 + tx * 4, p0 + 64 + tx * 4};
+
+  float acc[8][8];
+#pragma unroll
+  for (int a = 0; a < 8; ++a)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[a][c] = 0.0f;
+
+  // ---------------- spectral term: 2*m2 reduction steps whose A operand is the row's Z vector
+  if (p.Z != nullptr) {
+    const int J = 2 * p.m2;
+    const float* Zb = p.Z + (size_t)b * p.H * J * M;
+    const bool zvec = (M % 4 == 0) && aligned16(p.Z);
+    if (ROWVEC) {
+      const bool tvec = aligned16(p.T);
+      int hrow[2], wcol[2];
+      bool pv[2];
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        pv[g] = pg[g] < HW;               // W % 4 == 0 -> a 4-pixel group is all-valid or all-invalid
+        hrow[g] = pv[g] ? pg[g] / W : 0;
+        wcol[g] = pv[g] ? pg[g] % W : 0;
+      }
+#pragma unroll 2
+      for (int j = 0; j < J; ++j) {
+        float tb[8], za[2][8];
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          const float4 t4 = load4g(p.T + (size_t)j * W + wcol[g], pv[g] ? 4 : 0, tvec);
+          tb[g * 4 + 0] = t4.x; tb[g * 4 + 1] = t4.y; tb[g * 4 + 2] = t4.z; tb[g * 4 + 3] = t4.w;
+#pragma unroll
+          for (int og = 0; og < 2; ++og) {
+            const float4 z4 = load4g(Zb + ((size_t)hrow[g] * J + j) * M + oa[og], pv[g] ? clamp04(M - oa[og]) : 0, zvec);
+            za[g][og * 4 + 0] = z4.x; za[g][og * 4 + 1] = z4.y; za[g][og * 4 + 2] = z4.z; za[g][og * 4 + 3] = z4.w;
+          }
+        }
+#pragma unroll
+        for (int a = 0; a < 8; ++a)
+#pragma unroll
+          for (int c = 0; c < 8; ++c) acc[a][c] = fmaf(za[c >> 2][a], tb[c], acc[a][c]);
+      }
+    } else {
+      // generic W: every pixel of the micro tile may sit in a different row
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const int pp = pg[c >> 2] + (c & 3);
+        if (pp < HW) {
+          const int hh = pp / W, ww = pp % W;
+          for (int j = 0; j < J; ++j) {
+            const float t = __ldg(p.T + (size_t)j * W + ww);
+            const float* zr = Zb + ((size_t)hh * J + j) * M;
+#pragma unroll
+            for (int a = 0; a < 8; ++a) {
+              const int o = oa[a >> 2] + (a & 3);
+              if (o < M) acc[a][c] = fmaf(__ldg(zr + o), t, acc[a][c]);
+            }
+          }
+        }
+      }
+    }
+  }
+
+  // ---------------- channel GEMM: acc[o][p] += sum_i At[i][o] * xin[b][i][p]
+  if (K > 0) {
+    const bool avec = (p.lda % 4 == 0) && aligned16(p.At);
+    const bool bvec = (HW % 4 == 0) && aligned16(p.x0) && (p.x1 == nullptr || aligned16(p.x1));
+    const int nt = ceil_div(K, kBK);
+    float4 ra[2], rb[4];
+
+    auto load_tile = [&](int t) {
+      const int k0 = t * kBK;
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int f = tid + q * kGemmThreads;
+        const int kk = f >> 4, m4 = (f & 15) * 4;
+        const int k = k0 + kk;
+        const int nv = (k < K) ? clamp04(M - (m0 + m4)) : 0;
+        ra[q] = (nv > 0) ? load4g(p.At + (size_t)k * p.lda + m0 + m4, nv, avec) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int f = tid + q * kGemmThreads;
+        const int kk = f >> 5, n4 = (f & 31) * 4;
+        const int i = k0 + kk, pp = p0 + n4;
+        const int nv = (i < K) ? clamp04(HW - pp) : 0;
+        if (nv > 0) {
+          const float* src = (i < p.C0) ? p.x0 + ((size_t)b * p.C0 + i) * HW + pp
+                                        : p.x1 + ((size_t)b * p.C1 + (i - p.C0)) * HW + pp;
+          rb[q] = load4g(src, nv, bvec);
+        } else {
+          rb[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+    };
+    auto store_tile = [&](int buf) {
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int f = tid + q * kGemmThreads;
+        *reinterpret_cast<float4*>(&As[buf][f >> 4][(f & 15) * 4]) = ra[q];
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int f = tid + q * kGemmThreads;
+        *reinterpret_cast<float4*>(&Bs[buf][f >> 5][(f & 31) * 4]) = rb[q];
+      }
+    };
+
+    load_tile(0);
+    store_tile(0);
+    __syncthreads();
+    for (int t = 0; t < nt; ++t) {
+      const int buf = t & 1;
+      if (t + 1 < nt) load_tile(t + 1);
+#pragma unroll
+      for (int kk = 0; kk < kBK; ++kk) {
+        const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4]);
+        const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][kk][32 + ty * 4]);
+        const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
+        const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][kk][64 + tx * 4]);
+        const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int a = 0; a < 8; ++a)
+#pragma unroll
+          for (int c = 0; c < 8; ++c) acc[a][c] = fmaf(av[a], bv[c], acc[a][c]);
+      }
+      if (t + 1 < nt) store_tile(buf ^ 1);
+      __syncthreads();
+    }
+  }
+
+  // ---------------- epilogue: + bias + residual, optional pre-activation save, activation, store
+  const bool ovec = (HW % 4 == 0) && aligned16(p.out) && (p.res == nullptr || aligned16(p.res)) &&
+                    (p.pre == nullptr || aligned16(p.pre));
+#pragma unroll
+  for (int a = 0; a < 8; ++a) {
+    const int o = oa[a >> 2] + (a & 3);
+    if (o >= M) continue;
+    const float bv = (p.bias != nullptr) ? __ldg(p.bias + o) : 0.0f;
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      const int nv = clamp04(HW - pg[g]);
+      if (nv <= 0) continue;
+      const size_t off = ((size_t)b * M + o) * HW + pg[g];
+      float4 v = make_float4(acc[a][g * 4 + 0] + bv, acc[a][g * 4 + 1] + bv, acc[a][g * 4 + 2] + bv,
+                             acc[a][g * 4 + 3] + bv);
+      if (p.res != nullptr) {
+        const float4 r = load4g(p.res + off, nv, ovec);
+        v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+      }
+      if (p.pre != nullptr) store4g(p.pre + off, v, nv, ovec);
+      if (p.act == PDES_ACT_GELU) {
+        v.x = gelu_f(v.x); v.y = gelu_f(v.y); v.z = gelu_f(v.z); v.w = gelu_f(v.w);
+      }
+      store4g(p.out + off, v, nv, ovec);
+    }
+  }
+}
+
+}  // namespace
+}  // namespace pdes
+
+extern "C" {
+
+int pdes_inv_h(const float* P, int nsplit, int B, int C, int H, int m1, int m2, const float* tables, float* Z,
+               void* stream) {
+  using namespace pdes;
+  PDES_REQUIRE(P && tables && Z, PDES_ERR_ARG, "pdes_inv_h: null pointer");
+  PDES_REQUIRE(nsplit >= 1 && B > 0 && C > 0 && H > 0 && m1 > 0 && m2 > 0 && m1 <= H, PDES_ERR_ARG,
+               "pdes_inv_h: bad sizes");
+  PDES_REQUIRE(B <= 65535 && ceil_div(H, kInvHRows) <= 65535, PDES_ERR_UNSUPPORTED, "pdes_inv_h: grid too large");
+  const int K = 2 * m1;
+  const size_t per_l = (size_t)K * kInvHLd * sizeof(float2);
+  const size_t tw_bytes = (size_t)H * sizeof(float2);
+  const size_t budget = 96 * 1024;
+  PDES_REQUIRE(per_l + tw_bytes <= (size_t)kMaxDynSmem, PDES_ERR_UNSUPPORTED,
+               "pdes_inv_h: m1=%d H=%d needs too much shared memory", m1, H);
+  int LC = m2;
+  if ((size_t)LC * per_l + tw_bytes > budget) {
+    LC = (int)((budget > tw_bytes ? budget - tw_bytes : 0) / per_l);
+    if (LC < 1) LC = 1;
+  }
+  const size_t smem = (size_t)LC * per_l + tw_bytes;
+  auto kfn = k_inv_h;
+  if (smem > 48 * 1024) PDES_SET_SMEM(kfn, smem);
+  const dim3 grid((unsigned)ceil_div(C, 32), (unsigned)ceil_div(H, kInvHRows), (unsigned)B);
+  const TableLayout t = table_layout(H, 1, m1, m2);   // twh offset does not depend on W
+  PDES_LAUNCH(kfn, grid, dim3(32, kInvHRows), smem, stream, reinterpret_cast<const float2*>(P), nsplit, B, C, H, m1,
+              m2, LC, tables + t.twh, Z);
+  return check_launch("pdes_inv_h");
+}
+
+int pdes_inv_w_gemm(const float* Z, const float* At, int lda, const float* x0, int C0, const float* x1, int C1,
+                    const float* bias, const float* res, const float* tables, int backward_scale, float* out,
+                    float* pre, int B, int M, int H, int W, int m1, int m2, int act, void* stream) {
+  using namespace pdes;
+  PDES_REQUIRE(out != nullptr, PDES_ERR_ARG, "pdes_inv_w_gemm: null output");
+  PDES_REQUIRE(Z != nullptr || At != nullptr, PDES_ERR_ARG, "pdes_inv_w_gemm: neither spectral nor 1x1 term given");
+  PDES_REQUIRE(B > 0 && M > 0 && H > 0 && W > 0, PDES_ERR_ARG, "pdes_inv_w_gemm: non-positive size");
+  PDES_REQUIRE(B <= 65535 && ceil_div(M, kBM) <= 65535, PDES_ERR_UNSUPPORTED, "pdes_inv_w_gemm: grid too large");
+  PDES_REQUIRE(act == PDES_ACT_NONE || act == PDES_ACT_GELU, PDES_ERR_ARG, "pdes_inv_w_gemm: unknown activation %d", act);
+  if (Z != nullptr) {
+    PDES_REQUIRE(tables != nullptr, PDES_ERR_ARG, "pdes_inv_w_gemm: spectral term needs tables");
+    PDES_REQUIRE(m1 > 0 && m2 > 0 && m2 <= W / 2 + 1, PDES_ERR_ARG, "pdes_inv_w_gemm: modes out of range");
+  }
+  if (At != nullptr) {
+    PDES_REQUIRE(x0 != nullptr && C0 > 0 && C1 >= 0 && lda >= M, PDES_ERR_ARG, "pdes_inv_w_gemm: bad 1x1 operands");
+    PDES_REQUIRE((C1 == 0) == (x1 == nullptr), PDES_ERR_ARG, "pdes_inv_w_gemm: x1/C1 mismatch");
+  }
+  InvWParams p;
+  p.Z = Z; p.At = At; p.lda = lda; p.x0 = x0; p.C0 = C0; p.x1 = x1; p.C1 = C1; p.bias = bias; p.res = res;
+  p.T = nullptr;
+  if (Z != nullptr) {
+    const TableLayout t = table_layout(H, W, m1, m2);
+    p.T = tables + (backward_scale ? t.tinv_b : t.tinv_f);
+  }
+  p.out = out; p.pre = pre; p.M = M; p.H = H; p.W = W; p.m2 = m2; p.act = act;
+  const dim3 grid((unsigned)ceil_div(H * W, kBN), (unsigned)ceil_div(M, kBM), (unsigned)B);
+  if (W % 4 == 0) {
+    auto kfn = k_inv_w_gemm<true>;
+    PDES_LAUNCH(kfn, grid, dim3(kGemmThreads), 0, stream, p);
+  } else {
+    auto kfn = k_inv_w_gemm<false>;
+    PDES_LAUNCH(kfn, grid, dim3(kGemmThreads), 0, stream, p);
+  }
+  return check_launch("pdes_inv_w_gemm");
+}
+
+}  // extern "C"

@@ -1,0 +1,234 @@
+"""Parity checks of every C-ABI entry point against the float64 oracle, written once and run on both the CPU
+emulation build (tests/test_kernels_emu.py) and the real sm_100a library (tests/test_kernels_gpu.py).
+
+Tolerance: float32 kernels vs float64 oracle, relative L2 <= 1e-5 (BASELINE.json north_star: "fp32 forward
+outputs and gradients within relative L2 1e-5 per layer")."""
+from __future__ import annotations
+
+import numpy as np
+
+from oracle import spectral_oracle as so
+
+TOL = 1e-5
+
+# (B, C0, C1, Cout, H, W, m1, m2) -- small shapes with the reference's edge cases:
+SMALL_SHAPES = [
+    (2, 5, 0, 4, 12, 8, 3, 5),     # m2 = W/2+1 (Nyquist column kept), no conditioning channels
+    (2, 3, 1, 4, 8, 8, 5, 3),      # 2*m1 > H: second block overwrites first-block rows (proc_fno.py:266-269)
+    (1, 6, 2, 6, 16, 16, 4, 4),    # vector paths (W%4==0, M%... not multiple of 4)
+    (2, 4, 1, 8, 9, 7, 2, 3),      # odd H, odd W: scalar paths, ragged tiles
+    (1, 3, 0, 2, 6, 10, 6, 2),     # m1 = H
+    (3, 7, 1, 12, 20, 12, 4, 5),   # HW=240: pixel tile crosses image end, Cout multiple of 4
+]
+
+
+def _rng(seed):
+    return np.random.default_rng(seed)
+
+
+def _weights(rng, Cin, Cout, m1, m2):
+    def one():
+        return (rng.standard_normal((Cin, Cout, m1, m2)) + 1j * rng.standard_normal((Cin, Cout, m1, m2))) / np.sqrt(Cin)
+    return one().astype(np.complex64), one().astype(np.complex64)
+
+
+def check_dft_fwd(be, shape, herm=0):
+    B, C0, C1, _, H, W, m1, m2 = shape
+    rng = _rng(1)
+    x0 = rng.standard_normal((B, C0, H, W)).astype(np.float32)
+    x1 = rng.standard_normal((B, C1, H, W)).astype(np.float32) if C1 else None
+    tab = be.tables(H, W, m1, m2)
+    dx0, dx1 = be.upload(x0), (be.upload(x1) if C1 else None)
+    X = be.empty((B, C0 + C1, 2 * m1, m2), complex_=True)
+    be.check(be.lib.pdes_dft_fwd(be.ptr(dx0), C0, be.ptr(dx1), C1, B, H, W, m1, m2, be.ptr(tab), herm, be.ptr(X), be.stream))
+    xin = x0 if x1 is None else np.concatenate([x0, x1], axis=1)
+    ref = so.dft_fwd_pruned(xin, m1, m2, lscale=so.hermitian_scale(H, W, m2) if herm else None)
+    err = so.rel_l2(be.download(X), ref)
+    assert err < TOL, f"dft_fwd {shape} herm={herm}: rel L2 {err:.3e}"
+    return err
+
+
+def check_mix(be, shape):
+    B, C0, C1, Cout, H, W, m1, m2 = shape
+    Cin = C0 + C1
+    rng = _rng(2)
+    X = (rng.standard_normal((B, Cin, 2 * m1, m2)) + 1j * rng.standard_normal((B, Cin, 2 * m1, m2))).astype(np.complex64)
+    GO = (rng.standard_normal((B, Cout, 2 * m1, m2)) + 1j * rng.standard_normal((B, Cout, 2 * m1, m2))).astype(np.complex64)
+    w1, w2 = _weights(rng, Cin, Cout, m1, m2)
+    dX, dGO, dw1, dw2 = be.upload(X), be.upload(GO), be.upload(w1), be.upload(w2)
+    errs = {}
+    for nsplit in (1, min(3, Cin)):
+        P = be.empty((nsplit, B, Cout, 2 * m1, m2), complex_=True)
+        be.check(be.lib.pdes_mix_fwd(be.ptr(dX), be.ptr(dw1), be.ptr(dw2), be.ptr(P), nsplit, B, Cin, Cout, H, m1, m2, be.stream))
+        errs[f"fwd{nsplit}"] = so.rel_l2(be.download(P).sum(axis=0), so.mode_mix(X, w1, w2, H))
+    for nsplit in (1, min(2, Cout)):
+        P = be.empty((nsplit, B, C0, 2 * m1, m2), complex_=True)
+        be.check(be.lib.pdes_mix_dx(be.ptr(dGO), be.ptr(dw1), be.ptr(dw2), be.ptr(P), nsplit, B, Cin, Cout, C0, H, m1, m2, be.stream))
+        errs[f"dx{nsplit}"] = so.rel_l2(be.download(P).sum(axis=0), so.mode_mix_dx(GO, w1, w2, H)[:, :C0])
+    g1 = be.empty((Cin, Cout, m1, m2), complex_=True)
+    g2 = be.empty((Cin, Cout, m1, m2), complex_=True)
+    be.check(be.lib.pdes_mix_dw(be.ptr(dX), be.ptr(dGO), be.ptr(g1), be.ptr(g2), B, Cin, Cout, H, m1, m2, be.stream))
+    r1, r2 = so.mode_mix_dw(X, GO, H, m1)
+    errs["dw1"] = so.rel_l2(be.download(g1), r1)
+    errs["dw2"] = so.rel_l2(be.download(g2), r2)
+    for k, v in errs.items():
+        assert v < TOL, f"mix {k} {shape}: rel L2 {v:.3e}"
+    return errs
+
+
+def check_inverse(be, shape, with_gemm=True, act=1, backward_scale=0):
+    """K3a + K3b against the oracle: spectral inverse (+ 1x1 conv + bias + residual + GELU)."""
+    B, C0, C1, Cout, H, W, m1, m2 = shape
+    Cin = C0 + C1
+    rng = _rng(3)
+    nsplit = 2
+    P = (rng.standard_normal((nsplit, B, Cout, 2 * m1, m2)) + 1j * rng.standard_normal((nsplit, B, Cout, 2 * m1, m2))).astype(np.complex64)
+    x0 = rng.standard_normal((B, C0, H, W)).astype(np.float32)
+    x1 = rng.standard_normal((B, C1, H, W)).astype(np.float32) if C1 else None
+    wc = (rng.standard_normal((Cout, Cin)) / np.sqrt(Cin)).astype(np.float32)
+    bias = rng.standard_normal(Cout).astype(np.float32)
+    res = rng.standard_normal((B, Cout, H, W)).astype(np.float32)
+    tab = be.tables(H, W, m1, m2)
+    dP = be.upload(P)
+    Z = be.empty((B, H, 2 * m2, Cout))
+    be.check(be.lib.pdes_inv_h(be.ptr(dP), nsplit, B, Cout, H, m1, m2, be.ptr(tab), be.ptr(Z), be.stream))
+    dwc = be.upload(wc)
+    wct = be.empty((Cin, Cout))
+    be.check(be.lib.pdes_transpose(be.ptr(dwc), be.ptr(wct), Cout, Cin, be.stream))
+    assert np.array_equal(be.download(wct), wc.T)
+    dx0, dx1 = be.upload(x0), (be.upload(x1) if C1 else None)
+    dbias, dres = be.upload(bias), be.upload(res)
+    out = be.empty((B, Cout, H, W))
+    pre = be.empty((B, Cout, H, W))
+    if with_gemm:
+        be.check(be.lib.pdes_inv_w_gemm(be.ptr(Z), be.ptr(wct), Cout, be.ptr(dx0), C0, be.ptr(dx1), C1, be.ptr(dbias),
+                                        be.ptr(dres), be.ptr(tab), backward_scale, be.ptr(out), be.ptr(pre),
+                                        B, Cout, H, W, m1, m2, act, be.stream))
+    else:
+        be.check(be.lib.pdes_inv_w_gemm(be.ptr(Z), None, 0, None, 0, None, 0, None, None, be.ptr(tab), backward_scale,
+                                        be.ptr(out), None, B, Cout, H, W, m1, m2, act, be.stream))
+    O = P.astype(np.complex128).sum(axis=0)
+    lscale = np.ones(m2) if backward_scale else so.hermitian_scale(H, W, m2)
+    ref = so.inv_pruned(O, H, W, lscale)
+    if with_gemm:
+        xin = x0 if x1 is None else np.concatenate([x0, x1], axis=1)
+        ref = ref + np.einsum("oi,bihw->bohw", wc.astype(np.float64), xin) + bias[None, :, None, None] + res
+        e_pre = so.rel_l2(be.download(pre), ref)
+        assert e_pre < TOL, f"inverse pre {shape}: rel L2 {e_pre:.3e}"
+    refo = so.gelu(ref) if act == 1 else ref
+    err = so.rel_l2(be.download(out), refo)
+    assert err < TOL, f"inverse out {shape} gemm={with_gemm} act={act}: rel L2 {err:.3e}"
+    return err
+
+
+def check_pointwise(be, shape):
+    B, C0, C1, Cout, H, W, m1, m2 = shape
+    Cin = C0 + C1
+    rng = _rng(4)
+    g = rng.standard_normal((B, Cout, H, W)).astype(np.float32)
+    pre = (2.0 * rng.standard_normal((B, Cout, H, W))).astype(np.float32)
+    x0 = rng.standard_normal((B, C0, H, W)).astype(np.float32)
+    x1 = rng.standard_normal((B, C1, H, W)).astype(np.float32) if C1 else None
+    dg, dpre = be.upload(g), be.upload(pre)
+    gp = be.empty((B, Cout, H, W))
+    be.check(be.lib.pdes_act_bwd(be.ptr(dg), be.ptr(dpre), be.ptr(gp), g.size, 1, be.stream))
+    e1 = so.rel_l2(be.download(gp), g * so.gelu_grad(pre))
+    assert e1 < TOL, f"act_bwd {shape}: {e1:.3e}"
+    ws = be.empty((be.lib.pdes_wgrad_workspace_floats(B, Cout, Cin, H * W),))
+    dW = be.empty((Cout, Cin))
+    db = be.empty((Cout,))
+    dx0, dx1 = be.upload(x0), (be.upload(x1) if C1 else None)
+    be.check(be.lib.pdes_wgrad(be.ptr(dg), be.ptr(dx0), C0, be.ptr(dx1), C1, be.ptr(dW), be.ptr(db), be.ptr(ws),
+                               B, Cout, H * W, be.stream))
+    xin = x0 if x1 is None else np.concatenate([x0, x1], axis=1)
+    e2 = so.rel_l2(be.download(dW), np.einsum("bohw,bihw->oi", g.astype(np.float64), xin))
+    e3 = so.rel_l2(be.download(db), g.astype(np.float64).sum(axis=(0, 2, 3)))
+    assert e2 < TOL and e3 < TOL, f"wgrad {shape}: dW {e2:.3e} dbias {e3:.3e}"
+    return e1, e2, e3
+
+
+def block_inputs(shape, seed=5, reference_init=False):
+    B, C0, C1, Cout, H, W, m1, m2 = shape
+    Cin = C0 + C1
+    rng = _rng(seed)
+    d = dict(
+        h=rng.standard_normal((B, C0, H, W)).astype(np.float32),
+        vb=(rng.random((B, C1, H, W)) < 0.3).astype(np.float32) if C1 else None,
+        res=rng.standard_normal((B, Cout, H, W)).astype(np.float32),
+        g=rng.standard_normal((B, Cout, H, W)).astype(np.float32),
+        wc=((rng.random((Cout, Cin)) * 2 - 1) / np.sqrt(Cin)).astype(np.float32),
+        bias=((rng.random(Cout) * 2 - 1) / np.sqrt(Cin)).astype(np.float32),
+    )
+    if reference_init:
+        # the reference's init: scale * U[0,1) for re and im, scale = 1/(Cin*Cout)  (proc_fno.py:239-243)
+        sc = 1.0 / (Cin * Cout)
+        d["w1"] = (sc * (rng.random((Cin, Cout, m1, m2)) + 1j * rng.random((Cin, Cout, m1, m2)))).astype(np.complex64)
+        d["w2"] = (sc * (rng.random((Cin, Cout, m1, m2)) + 1j * rng.random((Cin, Cout, m1, m2)))).astype(np.complex64)
+    else:
+        d["w1"], d["w2"] = _weights(rng, Cin, Cout, m1, m2)
+    return d
+
+
+def run_block(be, shape, d, act=1, use_res=True, use_conv=True):
+    """Forward + backward of the fused chain; returns dict of numpy results."""
+    B, C0, C1, Cout, H, W, m1, m2 = shape
+    Cin = C0 + C1
+    lib = be.lib
+    tab = be.tables(H, W, m1, m2)
+    up = {k: (be.upload(v) if v is not None else None) for k, v in d.items()}
+    wct = None
+    if use_conv:
+        wct = be.empty((Cin, Cout))
+        be.check(lib.pdes_transpose(be.ptr(up["wc"]), be.ptr(wct), Cout, Cin, be.stream))
+    X = be.empty((B, Cin, 2 * m1, m2), complex_=True)
+    ws = be.empty((lib.pdes_block_fwd_workspace_floats(B, Cin, Cout, H, W, m1, m2),))
+    out = be.empty((B, Cout, H, W))
+    pre = be.empty((B, Cout, H, W))
+    be.check(lib.pdes_block_forward(be.ptr(up["h"]), C0, be.ptr(up["vb"]), C1, be.ptr(up["w1"]), be.ptr(up["w2"]),
+                                    be.ptr(wct), be.ptr(up["bias"]) if use_conv else None,
+                                    be.ptr(up["res"]) if use_res else None, be.ptr(tab), be.ptr(X), be.ptr(ws),
+                                    be.ptr(out), be.ptr(pre), B, Cout, H, W, m1, m2, act, be.stream))
+    wsb = be.empty((lib.pdes_block_bwd_workspace_floats(B, C0, C1, Cout, H, W, m1, m2),))
+    g_pre = be.empty((B, Cout, H, W))
+    dh = be.empty((B, C0, H, W))
+    gw1 = be.empty((Cin, Cout, m1, m2), complex_=True)
+    gw2 = be.empty((Cin, Cout, m1, m2), complex_=True)
+    dwc = be.empty((Cout, Cin))
+    dbias = be.empty((Cout,))
+    be.check(lib.pdes_block_backward(be.ptr(up["g"]), be.ptr(pre), be.ptr(up["h"]), C0, be.ptr(up["vb"]), C1,
+                                     be.ptr(X), be.ptr(up["w1"]), be.ptr(up["w2"]),
+                                     be.ptr(up["wc"]) if use_conv else None, be.ptr(tab), be.ptr(wsb),
+                                     be.ptr(g_pre), be.ptr(dh), be.ptr(gw1), be.ptr(gw2),
+                                     be.ptr(dwc) if use_conv else None, be.ptr(dbias) if use_conv else None,
+                                     B, Cout, H, W, m1, m2, act, be.stream))
+    r = dict(out=be.download(out), pre=be.download(pre), X=be.download(X), dh=be.download(dh),
+             dw1=be.download(gw1), dw2=be.download(gw2))
+    if act:
+        r["dres"] = be.download(g_pre)
+    if use_conv:
+        r["dwc"] = be.download(dwc)
+        r["dbias"] = be.download(dbias)
+    return r
+
+
+def check_block(be, shape, act=1, use_res=True, use_conv=True, reference_init=False, tol=TOL):
+    d = block_inputs(shape, reference_init=reference_init)
+    r = run_block(be, shape, d, act=act, use_res=use_res, use_conv=use_conv)
+    actn = "gelu" if act else None
+    wc = d["wc"] if use_conv else None
+    bias = d["bias"] if use_conv else None
+    res = d["res"] if use_res else None
+    out, pre, X = so.fno_block_forward(d["h"], d["vb"], d["w1"], d["w2"], wc, bias, res, actn)
+    ref = so.fno_block_backward(d["h"], d["vb"], d["w1"], d["w2"], wc, bias, res, actn, d["g"])
+    errs = dict(out=so.rel_l2(r["out"], out), X=so.rel_l2(r["X"], X), dh=so.rel_l2(r["dh"], ref["dh"]),
+                dw1=so.rel_l2(r["dw1"], ref["dw1"]), dw2=so.rel_l2(r["dw2"], ref["dw2"]))
+    if act:
+        errs["pre"] = so.rel_l2(r["pre"], pre)
+        if use_res:
+            errs["dres"] = so.rel_l2(r["dres"], ref["dres"])
+    if use_conv:
+        errs["dwc"] = so.rel_l2(r["dwc"], ref["dwc"])
+        errs["dbias"] = so.rel_l2(r["dbias"], ref["dbias"])
+    for k, v in errs.items():
+        assert v < tol, f"block {k} {shape} act={act} res={use_res} conv={use_conv}: rel L2 {v:.3e}"
+    return errs

@@ -1,0 +1,64 @@
+"""CPU suite: the CUDA kernel sources compiled for the CPU emulator, checked against the float64 oracle.
+This validates indexing, staging, guards and the math of every kernel without a GPU; the -m gpu tests repeat the
+same cases on the real sm_100a build."""
+import pytest
+
+import kernel_cases as kc
+from backends import EmuBackend
+
+
+@pytest.fixture(scope="module")
+def be():
+    return EmuBackend()
+
+
+@pytest.mark.parametrize("shape", kc.SMALL_SHAPES)
+@pytest.mark.parametrize("herm", [0, 1])
+def test_dft_fwd(be, shape, herm):
+    kc.check_dft_fwd(be, shape, herm)
+
+
+@pytest.mark.parametrize("shape", kc.SMALL_SHAPES)
+def test_mix(be, shape):
+    kc.check_mix(be, shape)
+
+
+@pytest.mark.parametrize("shape", kc.SMALL_SHAPES)
+def test_inverse_full(be, shape):
+    kc.check_inverse(be, shape, with_gemm=True, act=1)
+
+
+@pytest.mark.parametrize("shape", kc.SMALL_SHAPES[:3])
+def test_inverse_spectral_only(be, shape):
+    kc.check_inverse(be, shape, with_gemm=False, act=0, backward_scale=1)
+
+
+@pytest.mark.parametrize("shape", kc.SMALL_SHAPES)
+def test_pointwise(be, shape):
+    kc.check_pointwise(be, shape)
+
+
+@pytest.mark.parametrize("shape", kc.SMALL_SHAPES)
+def test_block_fwd_bwd(be, shape):
+    kc.check_block(be, shape, act=1, use_res=True, use_conv=True)
+
+
+def test_block_variants(be):
+    kc.check_block(be, kc.SMALL_SHAPES[2], act=0, use_res=False, use_conv=True)    # FNO layer without activation
+    kc.check_block(be, kc.SMALL_SHAPES[1], act=1, use_res=False, use_conv=True)    # pure FNO layer (GELU inside)
+    kc.check_block(be, kc.SMALL_SHAPES[0], act=0, use_res=False, use_conv=False)   # bare SpectralConv2d
+
+
+def test_bad_arguments_raise(be):
+    import numpy as np
+    lib = be.lib
+    x = be.upload(np.zeros((1, 1, 8, 8)))
+    X = be.empty((1, 1, 4, 6), complex_=True)
+    tab = be.tables(8, 8, 2, 2)
+    # m2 > W//2+1 must be rejected like the reference's assert (proc_fno.py:135-139)
+    with pytest.raises(ValueError):
+        be.check(lib.pdes_dft_fwd(be.ptr(x), 1, None, 0, 1, 8, 8, 2, 6, be.ptr(tab), 0, be.ptr(X), be.stream))
+    with pytest.raises(ValueError):
+        be.check(lib.pdes_dft_fwd(None, 1, None, 0, 1, 8, 8, 2, 2, be.ptr(tab), 0, be.ptr(X), be.stream))
+    with pytest.raises(ValueError):
+        be.check(lib.pdes_tables_fill(8, 8, 9, 2, x.ctypes.data))
