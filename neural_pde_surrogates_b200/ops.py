@@ -1,0 +1,216 @@
+"""torch.autograd binding of the sm_100a spectral-block kernels (the only compute path: no fallback).
+
+`fno_block(h, vb, res, w1, w2, wc, bias, act)` computes, in one chain of hand-written kernels,
+
+    act( SpectralConv2d(cat[h, vb]) + Conv2d_1x1(cat[h, vb]) + bias + res )
+
+which is the body of reference FNO_Layer.forward (proc_fno.py:133-155) plus the U-FNO block tail
+`activation(h_fno + h_unet)` (proc_ufno.py:111-118).  PyTorch is used for device memory, streams and autograd
+bookkeeping only; every arithmetic pass over the data is a kernel from csrc/.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _native
+
+ACT_NONE, ACT_GELU = _native.ACT_NONE, _native.ACT_GELU
+
+_tables_cache: dict = {}
+_wct_cache: dict = {}
+
+# ---- instrumentation used by bench.py: kernel-launch counter and in-situ CUDA-event timing of the two chains
+_counters = {"launches": 0}
+_timing = {"on": False, "block_forward": [], "block_backward": []}
+
+
+def reset_counters():
+    _counters["launches"] = 0
+
+
+def counters():
+    return dict(_counters)
+
+
+def enable_timing(flag: bool):
+    _timing["on"] = bool(flag)
+    if flag:
+        _timing["block_forward"], _timing["block_backward"] = [], []
+
+
+def collect_timings():
+    """Milliseconds per recorded chain launch (synchronises)."""
+    torch.cuda.synchronize()
+    return {k: [a.elapsed_time(b) for a, b in _timing[k]] for k in ("block_forward", "block_backward")}
+
+
+class _Timed:
+    def __init__(self, key):
+        self.key = key
+
+    def __enter__(self):
+        if _timing["on"]:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *a):
+        if _timing["on"]:
+            self.e1.record()
+            _timing[self.key].append((self.e0, self.e1))
+
+
+def _lib():
+    return _native.library()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def tables_for(device: torch.device, H: int, W: int, m1: int, m2: int) -> torch.Tensor:
+    """Device copy of the twiddle tables for one (H, W, m1, m2); built once in float64 on the host."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(), H, W, m1, m2)
+    t = _tables_cache.get(key)
+    if t is None:
+        lib = _lib()
+        n = lib.pdes_tables_floats(H, W, m1, m2)
+        if n == 0:
+            raise ValueError(f"invalid spectral shape H={H} W={W} modes=({m1},{m2})")
+        buf = np.zeros(n, dtype=np.float32)
+        _native.check(lib, lib.pdes_tables_fill(H, W, m1, m2, buf.ctypes.data))
+        t = torch.from_numpy(buf).to(device)
+        _tables_cache[key] = t
+    return t
+
+
+def _transposed_conv_weight(wc: torch.Tensor) -> torch.Tensor:
+    """[Cout, Cin(,1,1)] -> [Cin, Cout] with our own transpose kernel; cached until the parameter changes."""
+    Cout, Cin = wc.shape[0], wc.shape[1]
+    key = (wc.data_ptr(), wc.device.index)
+    hit = _wct_cache.get(key)
+    if hit is not None and hit[0] == wc._version and hit[1].shape == (Cin, Cout) and not torch.cuda.is_current_stream_capturing():
+        return hit[1]
+    wct = torch.empty(Cin, Cout, device=wc.device, dtype=torch.float32)
+    lib = _lib()
+    _native.check(lib, lib.pdes_transpose(wc.data_ptr(), wct.data_ptr(), Cout, Cin, _stream()))
+    _counters["launches"] += 1
+    if not torch.cuda.is_current_stream_capturing():
+        _wct_cache[key] = (wc._version, wct)
+    return wct
+
+
+def _check_f32_cuda(name, t, ndim=None):
+    if t is None:
+        return
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} is on {t.device}: the B200 spectral block only runs on CUDA (no CPU fallback)")
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name} must be float32 (the reference path is fp32-only, proc_fno.py:265), got {t.dtype}")
+    if ndim is not None and t.dim() != ndim:
+        raise ValueError(f"{name} must have {ndim} dims, got shape {tuple(t.shape)}")
+
+
+class FNOBlockFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, h, vb, res, w1, w2, wc, bias, act):
+        lib = _lib()
+        _check_f32_cuda("h", h, 4)
+        _check_f32_cuda("variables_broadcast", vb, 4)
+        _check_f32_cuda("residual", res, 4)
+        _check_f32_cuda("w.weight", wc)
+        _check_f32_cuda("w.bias", bias)
+        if w1.dtype != torch.complex64 or w2.dtype != torch.complex64:
+            raise TypeError("spectral weights must be complex64 (proc_fno.py:240-243)")
+        B, C0, H, W = h.shape
+        C1 = 0 if vb is None else vb.shape[1]
+        Cin, Cout, m1, m2 = w1.shape
+        if C0 + C1 != Cin:
+            raise ValueError(f"input has {C0}+{C1} channels but the spectral weights expect {Cin}")
+        # same checks as the asserts in FNO_Layer.forward (proc_fno.py:135-139)
+        assert m2 <= W // 2 + 1, 'modes should be at most the spatial dim // 2 + 1 for the last spatial dimension!'
+        assert m1 <= H, 'modes should be at most the spatial dim all but the last spatial dimensions!'
+        h = h.contiguous()
+        vb = None if vb is None else vb.contiguous()
+        res = None if res is None else res.contiguous()
+        w1c, w2c = w1.contiguous(), w2.contiguous()
+        dev = h.device
+        needs_grad = any(ctx.needs_input_grad)
+        with torch.cuda.device(dev):
+            tab = tables_for(dev, H, W, m1, m2)
+            wct = None
+            if wc is not None:
+                wc2 = wc.reshape(Cout, Cin)
+                if not wc2.is_contiguous():
+                    wc2 = wc2.contiguous()
+                wct = _transposed_conv_weight(wc2)
+            X = torch.empty(B, Cin, 2 * m1, m2, dtype=torch.complex64, device=dev)
+            out = torch.empty(B, Cout, H, W, dtype=torch.float32, device=dev)
+            pre = torch.empty_like(out) if (needs_grad and act != ACT_NONE) else None
+            ws = torch.empty(lib.pdes_block_fwd_workspace_floats(B, Cin, Cout, H, W, m1, m2), dtype=torch.float32, device=dev)
+            p = lambda t: None if t is None else t.data_ptr()
+            with _Timed("block_forward"):
+                _native.check(lib, lib.pdes_block_forward(
+                    p(h), C0, p(vb), C1, p(w1c), p(w2c), p(wct), p(bias), p(res), p(tab), p(X), p(ws), p(out), p(pre),
+                    B, Cout, H, W, m1, m2, act, _stream()))
+            _counters["launches"] += 4          # K1, K2, K3a, K3b
+        if needs_grad:
+            ctx.save_for_backward(h, vb, w1c, w2c, wc, X, pre)
+            ctx.act = act
+            ctx.has_res = res is not None
+            ctx.has_bias = bias is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib()
+        h, vb, w1, w2, wc, X, pre = ctx.saved_tensors
+        if ctx.needs_input_grad[1]:
+            raise NotImplementedError("gradient w.r.t. the broadcast conditioning channels is not implemented "
+                                      "(they never require grad in the twophase configs, enc_proc_dec.py:126-137)")
+        B, C0, H, W = h.shape
+        C1 = 0 if vb is None else vb.shape[1]
+        Cin, Cout, m1, m2 = w1.shape
+        g = g.contiguous()
+        dev = h.device
+        with torch.cuda.device(dev):
+            tab = tables_for(dev, H, W, m1, m2)
+            act = ctx.act
+            g_pre = torch.empty_like(g) if act != ACT_NONE else None
+            dh = torch.empty_like(h)
+            gw1, gw2 = torch.empty_like(w1), torch.empty_like(w2)
+            wc2 = dwc = dbias = None
+            if wc is not None:
+                wc2 = wc.reshape(Cout, Cin)
+                if not wc2.is_contiguous():
+                    wc2 = wc2.contiguous()
+                dwc = torch.empty(Cout, Cin, dtype=torch.float32, device=dev)
+                dbias = torch.empty(Cout, dtype=torch.float32, device=dev) if ctx.has_bias else None
+            ws = torch.empty(lib.pdes_block_bwd_workspace_floats(B, C0, C1, Cout, H, W, m1, m2), dtype=torch.float32, device=dev)
+            p = lambda t: None if t is None else t.data_ptr()
+            with _Timed("block_backward"):
+                _native.check(lib, lib.pdes_block_backward(
+                    p(g), p(pre), p(h), C0, p(vb), C1, p(X), p(w1), p(w2), p(wc2), p(tab), p(ws), p(g_pre), p(dh),
+                    p(gw1), p(gw2), p(dwc), p(dbias), B, Cout, H, W, m1, m2, act, _stream()))
+            # act_bwd, K1(g), mix_dw, mix_dx, K3a, K3b, wgrad + its reduce
+            _counters["launches"] += 5 + (1 if act != ACT_NONE else 0) + (2 if wc is not None else 0)
+        d_res = (g_pre if act != ACT_NONE else g) if ctx.has_res else None
+        return dh, None, d_res, gw1, gw2, (None if dwc is None else dwc.view_as(wc)), dbias, None
+
+
+def fno_block(h, vb, res, w1, w2, wc, bias, act: int = ACT_NONE):
+    """act(spectral(cat[h,vb]) + conv1x1(cat[h,vb]) + bias + res); any of vb / res / wc / bias may be None."""
+    return FNOBlockFunction.apply(h, vb, res, w1, w2, wc, bias, act)
+
+
+def act_code(module) -> int | None:
+    """Map an activation module to a kernel epilogue code; None means "apply it with torch after the kernel"."""
+    if module is None:
+        return ACT_NONE
+    if isinstance(module, torch.nn.GELU) and getattr(module, "approximate", "none") == "none":
+        return ACT_GELU
+    if isinstance(module, torch.nn.Identity):
+        return ACT_NONE
+    return None

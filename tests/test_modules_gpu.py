@@ -1,0 +1,144 @@
+"""-m gpu parity tests of the module API (the drop-in boundary): the CUDA path of SpectralConv2d / FNO_Layer / FNO /
+UFNO / the full model / the rollout, against (i) the golden fixtures produced by the unmodified reference and
+(ii) the CPU torch port with identical weights at larger shapes.  Tolerances from BASELINE.json north_star:
+fp32 forward and gradients rel L2 <= 1e-5 per layer, 50-step rollout <= 1e-4."""
+import copy
+
+import pytest
+import torch
+
+import neural_pde_surrogates_b200 as npb
+from parity_util import golden, grads_close, load_prefixed_state, rel_l2, tiny_model
+from neural_pde_surrogates_b200.trainer import AutoregressivePushforwardTrainer
+from oracle.torch_port import cpu_port
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(autouse=True)
+def strict_fp32():
+    torch.backends.cudnn.allow_tf32 = False           # cuDNN TF32 convs alone would break the 1e-5 bar
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+
+
+def test_spectral_conv2d_vs_reference_golden():
+    g = golden("spectral_conv2d.npz")
+    for n in range(int(g["n_cases"])):
+        w1 = g[f"c{n}_w1"]
+        Ci, Co, m1, m2 = w1.shape
+        conv = npb.SpectralConv2d(Ci, Co, (m1, m2))
+        conv.load_state_dict({"weights1": torch.from_numpy(w1), "weights2": torch.from_numpy(g[f"c{n}_w2"])})
+        conv = conv.to(DEV)
+        x = torch.from_numpy(g[f"c{n}_x"]).to(DEV).requires_grad_()
+        y = conv(x)
+        (y * torch.from_numpy(g[f"c{n}_g"]).to(DEV)).sum().backward()
+        assert rel_l2(y, g[f"c{n}_y"]) < 1e-5
+        assert rel_l2(x.grad, g[f"c{n}_gx"]) < 1e-5
+        assert rel_l2(conv.weights1.grad, g[f"c{n}_gw1"]) < 1e-5
+        assert rel_l2(conv.weights2.grad, g[f"c{n}_gw2"]) < 1e-5
+
+
+@pytest.mark.parametrize("name", ["ufno", "fno"])
+def test_processors_vs_reference_golden(name):
+    from test_oracle_golden import _processor
+    g = golden("processors.npz")
+    proc = load_prefixed_state(_processor(name), g, f"{name}_sd_").to(DEV)
+    h = torch.from_numpy(g[f"{name}_h"]).to(DEV).requires_grad_()
+    vb = torch.from_numpy(g[f"{name}_vb"]).to(DEV)
+    y = proc(h=h, variables_broadcast=vb, pos=None)
+    (y * torch.from_numpy(g[f"{name}_g"]).to(DEV)).sum().backward()
+    assert rel_l2(y, g[f"{name}_y"]) < 1e-5
+    assert rel_l2(h.grad, g[f"{name}_gh"]) < 1e-5
+    grads_close(proc.named_parameters(), lambda k: g[f"{name}_grad_{k}"], 2e-5)
+
+
+def test_full_model_train_step_and_rollout_vs_reference_golden():
+    model, pde, g = tiny_model(DEV)
+    B = g["u"].shape[0]
+    u, mask, labels = (torch.from_numpy(g[k]).to(DEV) for k in ("u", "mask", "labels"))
+    pos = pde.x.to(DEV)[None].repeat(B, 1, 1, 1)
+    tr = AutoregressivePushforwardTrainer(model, pde, device=DEV, batch_size=B, base_resolution=(501, 24, 16))
+    loss, pred = tr.train_step_windows(u, labels, pos, torch.empty(B, 0, device=DEV), mask)
+    loss.backward()
+    assert rel_l2(pred, g["y"]) < 1e-5
+    grads_close(model.named_parameters(), lambda k: g[f"grad_{k}"], 5e-5)
+    for graph in (False, True):
+        with torch.no_grad():
+            preds = tr.simulate(u, torch.empty(B, 0, device=DEV), pos, compute_loss=False, include_data=True, nr_gt_steps=1,
+                                t_res=150, spatial_conditioning=mask, use_bc=False, divide_by_t=False, graph=graph)
+        for s in range(5):
+            assert rel_l2(preds[s + 1], g["rollout"][s]) < 1e-4, (graph, s)
+
+
+def _cfg_model(hidden_features, fno_modes, hidden_blocks, H, W, processor="UFNO"):
+    torch.manual_seed(42)
+    pde = npb.TwoPhasePDE(H, W)
+    return npb.build_twophase_model(pde=pde, processor=copy.deepcopy(processor), hidden_features=hidden_features,
+                                    fno_modes=fno_modes, hidden_blocks=hidden_blocks), pde
+
+
+@pytest.mark.parametrize("processor", ["UFNO", [dict(object="FNO", hidden_blocks=1), dict(object="UFNO", hidden_blocks=1)]])
+def test_config_shape_block_parity_vs_cpu_port(processor):
+    """Config grid 96x64, modes 10, width 64 (width reduced so the CPU port finishes in seconds): forward + every
+    gradient of the whole model, CUDA path vs CPU port with identical weights and the reference's own init."""
+    model, pde = _cfg_model(64, 10, 1, 96, 64, processor)
+    gpu_model = copy.deepcopy(model).to(DEV)
+    B = 2
+    torch.manual_seed(1)
+    u = torch.rand(B, 1, 25, 96, 64) * 0.5 + 0.1
+    labels = torch.rand(B, 1, 25, 96, 64) * 0.5 + 0.1
+    mask = (torch.rand(B, 1, 96, 64) < 0.1).float()
+    pos = pde.x[None].repeat(B, 1, 1, 1)
+    crit = torch.nn.MSELoss(reduction="sum")
+    with cpu_port():
+        y_cpu = model(u, cond=torch.empty(B, 0), bc=None, pos=pos, t_cond=None, spatial_cond=mask)
+        torch.sqrt(crit(y_cpu, labels)).backward()
+    y = gpu_model(u.to(DEV), cond=torch.empty(B, 0, device=DEV), bc=None, pos=pos.to(DEV), t_cond=None, spatial_cond=mask.to(DEV))
+    torch.sqrt(crit(y, labels.to(DEV))).backward()
+    assert rel_l2(y, y_cpu) < 1e-5
+    ref = dict(model.named_parameters())
+    grads_close(gpu_model.named_parameters(), lambda k: ref[k].grad, 5e-5)
+
+
+def test_fifty_step_rollout_vs_cpu_port():
+    """BASELINE config 4: 50-step autoregressive rollout, rel L2 <= 1e-4 at every step (twophase_no_obstacle: mask = 0)."""
+    model, pde = _cfg_model(32, 10, 2, 96, 64)
+    model.eval()
+    gpu_model = copy.deepcopy(model).to(DEV)
+    B = 2
+    torch.manual_seed(2)
+    u = torch.rand(B, 1, 25, 96, 64) * 0.5 + 0.1
+    mask = torch.zeros(B, 1, 96, 64)
+    pos = pde.x[None].repeat(B, 1, 1, 1)
+    kw = dict(compute_loss=False, include_data=True, nr_gt_steps=1, t_res=25 * 51, use_bc=False, divide_by_t=False)
+    tr_cpu = AutoregressivePushforwardTrainer(model, pde, device="cpu", batch_size=B)
+    tr_gpu = AutoregressivePushforwardTrainer(gpu_model, pde, device=DEV, batch_size=B)
+    with torch.no_grad():
+        with cpu_port():
+            ref = tr_cpu.simulate(u, torch.empty(B, 0), pos, spatial_conditioning=mask, **kw)
+        out = tr_gpu.simulate(u.to(DEV), torch.empty(B, 0, device=DEV), pos.to(DEV), spatial_conditioning=mask.to(DEV),
+                              graph=True, **kw)
+    assert len(out) == 51
+    worst = max(rel_l2(o, r) for o, r in zip(out[1:], ref[1:]))
+    assert worst < 1e-4, worst
+
+
+def test_layer_options_and_errors():
+    # conv_mode="double" and kernel_size=3 keep working (local convs on cuDNN, spectral + activation fused)
+    torch.manual_seed(0)
+    x = torch.randn(2, 6, 16, 16)
+    for kw in (dict(conv_mode="double", kernel_size=3), dict(kernel_size=3), dict(activation=torch.nn.Tanh)):
+        layer = npb.FNO_Layer(hidden_dim=6, num_spatial_dims=2, modes=4, **kw)
+        with cpu_port():
+            ref = layer(x)
+        out = copy.deepcopy(layer).to(DEV)(x.to(DEV))
+        assert rel_l2(out, ref) < 1e-5, kw
+    layer = npb.FNO_Layer(hidden_dim=4, num_spatial_dims=2, modes=10).to(DEV)
+    with pytest.raises(AssertionError):                     # modes > W//2+1 (proc_fno.py:135-139)
+        layer(torch.randn(1, 4, 16, 16, device=DEV))
+    with pytest.raises(TypeError):
+        npb.SpectralConv2d(4, 4, (2, 2)).to(DEV)(torch.randn(1, 4, 8, 8, device=DEV, dtype=torch.float64))
+    with pytest.raises(NotImplementedError):
+        npb.FNO_Layer(hidden_dim=4, num_spatial_dims=1, modes=4)
