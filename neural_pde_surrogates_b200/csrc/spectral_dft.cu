@@ -6,6 +6,7 @@
 // The image is read from HBM exactly once (coalesced 128-bit loads); everything else stays on chip.
 // Generic in (H, W, m1, m2): rows are processed in chunks of R so that large grids still fit.
 #include "pdes_common.cuh"
+#include "pdes_ptx.cuh"
 
 namespace pdes {
 namespace {
@@ -120,6 +121,140 @@ k_dft_fwd(const float* __restrict__ x0, int C0, const float* __restrict__ x1, in
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// Fast path for the shipped config (H=96, W=64, modes 10x10): one 64-thread CTA per image.
+//   * the image arrives with ONE bulk async copy (TMA 1-D, SASS UBLKCP) signalled on an mbarrier;
+//   * stage 1 (H axis): thread = column w.  Real input => rows +kx and -kx share their sums: P = sum x cos,
+//     Q = sum x sin for kx = 0..m1, with h and H-h folded (cos even, sin odd).  All twiddles are compile-time
+//     constants (immediates), the loop is fully unrolled: ~1000 FFMA-imm per column, no table loads;
+//   * stage 2 (W axis): 110 work items (kx, l), each four real dot products over w; X[+kx] and X[-kx] come out
+//     of the same four sums.
+// ~4x fewer instructions per image than the generic kernel.
+namespace ct {
+constexpr double kPi = 3.14159265358979323846264338327950288;
+constexpr double sin_taylor(double x) {
+  double t = x, s = x;
+  for (int n = 1; n <= 20; ++n) { t *= -x * x / ((2.0 * n) * (2.0 * n + 1.0)); s += t; }
+  return s;
+}
+constexpr double cos_taylor(double x) {
+  double t = 1.0, s = 1.0;
+  for (int n = 1; n <= 20; ++n) { t *= -x * x / ((2.0 * n - 1.0) * (2.0 * n)); s += t; }
+  return s;
+}
+template <int N> struct Tw { float c[N]; float s[N]; };
+template <int N> constexpr Tw<N> make_tw() {
+  Tw<N> t{};
+  for (int j = 0; j < N; ++j) {
+    double a = 2.0 * kPi * j / N;
+    if (a > kPi) a -= 2.0 * kPi;
+    t.c[j] = (float)cos_taylor(a);
+    t.s[j] = (float)sin_taylor(a);
+  }
+  return t;
+}
+}  // namespace ct
+
+__device__ constexpr ct::Tw<96> kTw96 = ct::make_tw<96>();
+
+template <int H, int W, int M1, int M2>
+__global__ void __launch_bounds__(W)
+k_dft_fwd_fast(const float* __restrict__ x0, int C0, const float* __restrict__ x1, int C1,
+               const float* __restrict__ twa_g, int nc4, const float* __restrict__ lscale, float* __restrict__ X) {
+  static_assert(H == 96, "twiddle table instantiated for H = 96");
+  static_assert(H % 2 == 0 && 2 * M1 <= H && M2 <= W / 2 + 1, "fast path preconditions");
+  constexpr int NK = M1 + 1;                 // |kx| = 0 .. M1
+  __align__(128) __shared__ float img[H * W];
+  __shared__ float pq[2][NK][W + 1];
+  __shared__ float2 tw2[M2][W + 1];
+  __align__(8) __shared__ unsigned long long mbar;
+
+  const int tid = threadIdx.x;
+  const int C = C0 + C1;
+  const int im = blockIdx.x;
+  const int b = im / C, c = im % C;
+  const float* src = (c < C0) ? x0 + ((size_t)b * C0 + c) * H * W : x1 + ((size_t)b * C1 + (c - C0)) * H * W;
+
+#ifndef PDES_CPU_EMU
+  if (tid == 0) {
+    ptx::mbar_init(&mbar, 1);
+    ptx::fence_mbar_init();
+    ptx::mbar_arrive_expect_tx(&mbar, H * W * 4);
+    ptx::bulk_g2s(img, src, H * W * 4, &mbar);
+  }
+#else
+  (void)mbar;
+  for (int i = tid; i < H * W; i += W) img[i] = src[i];
+#endif
+  for (int i = tid; i < M2 * W; i += W) {
+    const int l = i / W, w = i % W;
+    tw2[l][w] = make_float2(__ldg(twa_g + w * nc4 + 2 * l), -__ldg(twa_g + w * nc4 + 2 * l + 1));
+  }
+  __syncthreads();                            // mbarrier init + tw2 visible to everyone
+#ifndef PDES_CPU_EMU
+  ptx::mbar_wait(&mbar, 0);
+#endif
+
+  // ---- stage 1: column DFT with +-kx pairing and h folding, compile-time twiddles
+  {
+    const float* col = img + tid;
+    float P[NK], Q[NK];
+    const float v0 = col[0], vh = col[(H / 2) * W];
+#pragma unroll
+    for (int kx = 0; kx < NK; ++kx) {
+      P[kx] = (kx & 1) ? (v0 - vh) : (v0 + vh);
+      Q[kx] = 0.0f;
+    }
+#pragma unroll
+    for (int h = 1; h < H / 2; ++h) {
+      const float a = col[h * W], bq = col[(H - h) * W];
+      const float e = a + bq, o = a - bq;
+#pragma unroll
+      for (int kx = 0; kx < NK; ++kx) {
+        P[kx] = fmaf(e, kTw96.c[(kx * h) % H], P[kx]);
+        if (kx > 0) Q[kx] = fmaf(o, kTw96.s[(kx * h) % H], Q[kx]);
+      }
+    }
+#pragma unroll
+    for (int kx = 0; kx < NK; ++kx) {
+      pq[0][kx][tid] = P[kx];
+      pq[1][kx][tid] = Q[kx];
+    }
+  }
+  __syncthreads();
+
+  // ---- stage 2: row DFT of (P -+ iQ) to the M2 kept columns
+  float* Xo = X + (size_t)im * (2 * M1 * M2) * 2;
+  for (int item = tid; item < NK * M2; item += W) {
+    const int kxi = item / M2, l = item % M2;
+    const float* pp = pq[0][kxi];
+    const float* qq = pq[1][kxi];
+    const float2* tt = tw2[l];
+    float a = 0.f, bs = 0.f, cq = 0.f, d = 0.f;
+#pragma unroll 8
+    for (int w = 0; w < W; ++w) {
+      const float p = pp[w], q = qq[w];
+      const float2 t = tt[w];
+      a = fmaf(p, t.x, a);
+      bs = fmaf(p, t.y, bs);
+      cq = fmaf(q, t.x, cq);
+      d = fmaf(q, t.y, d);
+    }
+    const float sc = (lscale != nullptr) ? __ldg(lscale + l) : 1.0f;
+    if (kxi < M1) {                          // +kx -> row k = kx:  sum (P - iQ)(c - is)
+      float* o = Xo + ((size_t)kxi * M2 + l) * 2;
+      o[0] = sc * (a - d);
+      o[1] = -sc * (bs + cq);
+    }
+    if (kxi > 0) {                           // -kx -> row k = 2*M1 - kx:  sum (P + iQ)(c - is)
+      float* o = Xo + ((size_t)(2 * M1 - kxi) * M2 + l) * 2;
+      o[0] = sc * (a + d);
+      o[1] = sc * (cq - bs);
+    }
+  }
+}
+
 }  // namespace
 }  // namespace pdes
 
@@ -132,6 +267,12 @@ extern "C" int pdes_dft_fwd(const float* x0, int C0, const float* x1, int C1, in
   PDES_REQUIRE(m1 > 0 && m2 > 0 && m1 <= H && m2 <= W / 2 + 1, PDES_ERR_ARG,
                "modes (%d,%d) exceed the grid (%d,%d): need m1 <= H and m2 <= W/2+1", m1, m2, H, W);
   const TableLayout t = table_layout(H, W, m1, m2);
+  if (H == 96 && W == 64 && m1 == 10 && m2 == 10 && aligned16(x0) && (x1 == nullptr || aligned16(x1))) {
+    auto kfast = k_dft_fwd_fast<96, 64, 10, 10>;
+    PDES_LAUNCH(kfast, dim3((unsigned)(B * (C0 + C1))), dim3(64), 0, stream, x0, C0, x1, C1, tables + t.twa, t.nc4,
+                herm_scale ? tables + t.herm : nullptr, X);
+    return check_launch("pdes_dft_fwd(fast)");
+  }
   const int xs_stride = (W % 2 == 0) ? W + 1 : W;
   const size_t fixed = (size_t)W * t.nc4 + round4((size_t)H * 2 * m2) + round4((size_t)2 * H);
   auto bytes_for = [&](int R) { return (round4((size_t)R * xs_stride) + fixed) * sizeof(float); };

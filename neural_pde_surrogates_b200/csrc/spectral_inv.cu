@@ -13,58 +13,99 @@ namespace pdes {
 namespace {
 
 // ------------------------------------------------------------------------------------------------- K3a
-constexpr int kInvHRows = 8;      // rows of h per CTA (one per warp)
-constexpr int kInvHLd = 33;       // padded channel stride (in float2) of the shared tile
+// One CTA = (b, 8 channels): the 8 x (2*m1*m2) spectrum tile is summed over the K2 split partials ONCE into shared
+// memory (coalesced along the mode index), then every thread owns one channel and HT rows h and accumulates LCH
+// columns at a time: per k it loads HT twiddles (warp-broadcast) and LCH spectrum values for 4*HT*LCH FMAs.
+constexpr int kIhOT = 8;                    // channels per CTA (=> 32-byte output sectors)
+constexpr int kIhHG = 32;                   // threads per channel; thread owns rows hg, hg+32, ...
+constexpr int kIhThreads = kIhOT * kIhHG;
+constexpr int kIhLd = kIhOT + 1;            // padded channel stride (float2) of the shared tile
 
-__global__ void __launch_bounds__(32 * kInvHRows)
-k_inv_h(const float2* __restrict__ P, int nsplit, int B, int C, int H, int m1, int m2, int LC,
+template <int HT, int LCH>
+__global__ void __launch_bounds__(kIhThreads)
+k_inv_h(const float2* __restrict__ P, int nsplit, int B, int C, int H, int m1, int m2,
         const float* __restrict__ twh_g, float* __restrict__ Z) {
   PDES_DYN_SMEM(float2, smem2);
-  const int K = 2 * m1;
-  float2* Os = smem2;                               // [K][LC][kInvHLd]
-  float2* twh = Os + (size_t)K * LC * kInvHLd;      // [H]
-  const int lane = threadIdx.x, wy = threadIdx.y;
-  const int tid = wy * 32 + lane, nt = 32 * kInvHRows;
-  const int c0 = blockIdx.x * 32;
-  const int h = blockIdx.y * kInvHRows + wy;
-  const int b = blockIdx.z;
-  const int J = 2 * m2;
+  const int K = 2 * m1, M2 = K * m2, J = 2 * m2;
+  float2* Os = smem2;                               // [M2][kIhLd]
+  float2* twh = Os + (size_t)M2 * kIhLd;            // [H]
+  const int tid = threadIdx.x;
+  const int ot = tid % kIhOT, hg = tid / kIhOT;
+  const int c0 = blockIdx.x * kIhOT, b = blockIdx.y;
 
-  for (int i = tid; i < H; i += nt) twh[i] = make_float2(__ldg(twh_g + 2 * i), __ldg(twh_g + 2 * i + 1));
+  for (int i = tid; i < H; i += kIhThreads) twh[i] = make_float2(__ldg(twh_g + 2 * i), __ldg(twh_g + 2 * i + 1));
+  for (int idx = tid; idx < kIhOT * M2; idx += kIhThreads) {
+    const int oo = idx / M2, m = idx - oo * M2;
+    float2 v = make_float2(0.f, 0.f);
+    if (c0 + oo < C) {
+      const float2* src = P + ((size_t)b * C + c0 + oo) * M2 + m;
+      for (int s = 0; s < nsplit; ++s) {
+        const float2 pv = __ldg(src + (size_t)s * B * C * M2);
+        v.x += pv.x; v.y += pv.y;
+      }
+    }
+    Os[(size_t)m * kIhLd + oo] = v;
+  }
+  __syncthreads();
 
-  for (int l0 = 0; l0 < m2; l0 += LC) {
-    const int lcn = (m2 - l0 < LC) ? (m2 - l0) : LC;
-    __syncthreads();
-    const int total = 32 * K * lcn;
-    for (int idx = tid; idx < total; idx += nt) {
-      const int lc = idx % lcn;
-      const int k = (idx / lcn) % K;
-      const int oo = idx / (lcn * K);
-      const int c = c0 + oo;
-      float2 v = make_float2(0.f, 0.f);
-      if (c < C) {
-        for (int s = 0; s < nsplit; ++s) {
-          const float2 pv = __ldg(P + ((((size_t)s * B + b) * C + c) * K + k) * m2 + l0 + lc);
-          v.x += pv.x; v.y += pv.y;
+  const bool cvalid = c0 + ot < C;
+  for (int hbase = 0; hbase < H; hbase += kIhHG * HT) {
+    for (int l0 = 0; l0 < m2; l0 += LCH) {
+      float ar[LCH][HT], ai[LCH][HT];
+#pragma unroll
+      for (int q = 0; q < LCH; ++q)
+#pragma unroll
+        for (int i = 0; i < HT; ++i) ar[q][i] = ai[q][i] = 0.0f;
+      // twiddle index of (k, h0) and its increment per 32 rows, advanced incrementally: kx grows by 1 per k
+      // inside each half, so no integer division in the loop (only at k = 0 and k = m1)
+      const unsigned h0m = (unsigned)(hbase + hg) % (unsigned)H, s32 = (unsigned)kIhHG % (unsigned)H;
+      unsigned j0 = 0, step = 0;
+      for (int k = 0; k < K; ++k) {
+        if (k == m1) {
+          const unsigned kx = (unsigned)kx_of(k, m1, H);
+          j0 = (unsigned)(((unsigned long long)kx * h0m) % (unsigned)H);
+          step = (unsigned)(((unsigned long long)kx * s32) % (unsigned)H);
+        }
+        float2 t[HT];                                     // e^{+i theta} = (cos, sin)
+        unsigned j = j0;
+#pragma unroll
+        for (int i = 0; i < HT; ++i) {
+          t[i] = twh[j];
+          j += step;
+          if (j >= (unsigned)H) j -= (unsigned)H;
+        }
+        j0 += h0m;
+        if (j0 >= (unsigned)H) j0 -= (unsigned)H;
+        step += s32;
+        if (step >= (unsigned)H) step -= (unsigned)H;
+        const float2* orow = Os + (size_t)(k * m2 + l0) * kIhLd + ot;
+#pragma unroll
+        for (int q = 0; q < LCH; ++q) {
+          if (l0 + q < m2) {
+            const float2 o = orow[(size_t)q * kIhLd];
+#pragma unroll
+            for (int i = 0; i < HT; ++i) {
+              ar[q][i] = fmaf(o.x, t[i].x, fmaf(-o.y, t[i].y, ar[q][i]));
+              ai[q][i] = fmaf(o.x, t[i].y, fmaf(o.y, t[i].x, ai[q][i]));
+            }
+          }
         }
       }
-      Os[((size_t)k * LC + lc) * kInvHLd + oo] = v;
-    }
-    __syncthreads();
-    if (h < H && c0 + lane < C) {
-      for (int lc = 0; lc < lcn; ++lc) {
-        float ar = 0.f, ai = 0.f;
-        for (int k = 0; k < K; ++k) {
-          const int kx = kx_of(k, m1, H);
-          const int j = (int)(((long)kx * h) % H);
-          const float2 t = twh[j];                                  // e^{+i theta} = (cos, sin)
-          const float2 o = Os[((size_t)k * LC + lc) * kInvHLd + lane];
-          ar = fmaf(o.x, t.x, fmaf(-o.y, t.y, ar));
-          ai = fmaf(o.x, t.y, fmaf(o.y, t.x, ai));
+      if (cvalid) {
+#pragma unroll
+        for (int i = 0; i < HT; ++i) {
+          const int h = hbase + hg + i * kIhHG;
+          if (h < H) {
+#pragma unroll
+            for (int q = 0; q < LCH; ++q) {
+              if (l0 + q < m2) {
+                float* z = Z + (((size_t)b * H + h) * J + 2 * (l0 + q)) * C + c0 + ot;
+                z[0] = ar[q][i];
+                z[C] = ai[q][i];
+              }
+            }
+          }
         }
-        float* z = Z + (((size_t)b * H + h) * J + 2 * (l0 + lc)) * C + c0 + lane;
-        z[0] = ar;
-        z[C] = ai;
       }
     }
   }
@@ -288,25 +329,26 @@ int pdes_inv_h(const float* P, int nsplit, int B, int C, int H, int m1, int m2, 
   PDES_REQUIRE(P && tables && Z, PDES_ERR_ARG, "pdes_inv_h: null pointer");
   PDES_REQUIRE(nsplit >= 1 && B > 0 && C > 0 && H > 0 && m1 > 0 && m2 > 0 && m1 <= H, PDES_ERR_ARG,
                "pdes_inv_h: bad sizes");
-  PDES_REQUIRE(B <= 65535 && ceil_div(H, kInvHRows) <= 65535, PDES_ERR_UNSUPPORTED, "pdes_inv_h: grid too large");
-  const int K = 2 * m1;
-  const size_t per_l = (size_t)K * kInvHLd * sizeof(float2);
-  const size_t tw_bytes = (size_t)H * sizeof(float2);
-  const size_t budget = 96 * 1024;
-  PDES_REQUIRE(per_l + tw_bytes <= (size_t)kMaxDynSmem, PDES_ERR_UNSUPPORTED,
-               "pdes_inv_h: m1=%d H=%d needs too much shared memory", m1, H);
-  int LC = m2;
-  if ((size_t)LC * per_l + tw_bytes > budget) {
-    LC = (int)((budget > tw_bytes ? budget - tw_bytes : 0) / per_l);
-    if (LC < 1) LC = 1;
-  }
-  const size_t smem = (size_t)LC * per_l + tw_bytes;
-  auto kfn = k_inv_h;
-  if (smem > 48 * 1024) PDES_SET_SMEM(kfn, smem);
-  const dim3 grid((unsigned)ceil_div(C, 32), (unsigned)ceil_div(H, kInvHRows), (unsigned)B);
+  PDES_REQUIRE(B <= 65535, PDES_ERR_UNSUPPORTED, "pdes_inv_h: grid too large");
+  const size_t smem = ((size_t)2 * m1 * m2 * kIhLd + (size_t)H) * sizeof(float2);
+  PDES_REQUIRE(smem <= (size_t)kMaxDynSmem, PDES_ERR_UNSUPPORTED,
+               "pdes_inv_h: modes (%d,%d) with H=%d need %zu B of shared memory", m1, m2, H, smem);
+  const dim3 grid((unsigned)ceil_div(C, kIhOT), (unsigned)B);
   const TableLayout t = table_layout(H, 1, m1, m2);   // twh offset does not depend on W
-  PDES_LAUNCH(kfn, grid, dim3(32, kInvHRows), smem, stream, reinterpret_cast<const float2*>(P), nsplit, B, C, H, m1,
-              m2, LC, tables + t.twh, Z);
+  const float2* P2 = reinterpret_cast<const float2*>(P);
+#define PDES_INVH_LAUNCH(HT, LCH)                                                                        \
+  do {                                                                                                   \
+    auto kfn = k_inv_h<HT, LCH>;                                                                         \
+    if (smem > 48 * 1024) PDES_SET_SMEM(kfn, smem);                                                      \
+    PDES_LAUNCH(kfn, grid, dim3(kIhThreads), smem, stream, P2, nsplit, B, C, H, m1, m2, tables + t.twh, Z); \
+  } while (0)
+  const int ht = H <= kIhHG * 3 ? 3 : (H <= kIhHG * 4 ? 4 : 8);
+  if (m2 % 5 == 0) {
+    if (ht == 3) PDES_INVH_LAUNCH(3, 5); else if (ht == 4) PDES_INVH_LAUNCH(4, 5); else PDES_INVH_LAUNCH(8, 5);
+  } else {
+    if (ht == 3) PDES_INVH_LAUNCH(3, 4); else if (ht == 4) PDES_INVH_LAUNCH(4, 4); else PDES_INVH_LAUNCH(8, 4);
+  }
+#undef PDES_INVH_LAUNCH
   return check_launch("pdes_inv_h");
 }
 

@@ -19,6 +19,7 @@ SMALL_SHAPES = [
     (2, 4, 1, 8, 9, 7, 2, 3),      # odd H, odd W: scalar paths, ragged tiles
     (1, 3, 0, 2, 6, 10, 6, 2),     # m1 = H
     (3, 7, 1, 12, 20, 12, 4, 5),   # HW=240: pixel tile crosses image end, Cout multiple of 4
+    (1, 3, 1, 4, 96, 64, 10, 10),  # the shipped grid / modes: takes the specialised K1 fast path
 ]
 
 
