@@ -148,7 +148,7 @@ def run_reference(args):
 
 def workload_config(B, n):
     return {"workload": "cfg_twophase_ufno train step (U-FNO x3, width 192, modes 10x10, grid 96x64, tw 25, Cin 193, Adam, unroll u=0)",
-            "per_gpu_batch": B, "global_batch": B * n, "parallelism": f"dp{n}", "grid": [H, W], "precision": "fp32, cuDNN TF32 off",
+            "per_gpu_batch": B, "global_batch": B * n, "parallelism": f"dp{n}", "grid": [H, W], "precision": "fp32 (cuDNN TF32 off, cudnn.benchmark on; spectral block 3xTF32 split on tcgen05 = fp32-faithful)",
             "l2_policy": "inputs+weights+activations per step (~1 GB) exceed the 126 MB L2; no explicit flush"}
 
 
@@ -191,6 +191,7 @@ def run_ours(args):
     torch.cuda.set_device(dev)
     torch.backends.cudnn.allow_tf32 = args.tf32_convs
     torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.benchmark = not args.no_cudnn_benchmark
     B = args.batch
 
     model, pde = build(dev)
@@ -322,6 +323,8 @@ def main():
     ap.add_argument("--batch", type=int, default=16, help="per-GPU batch (config default, defaults/base.py:6)")
     ap.add_argument("--rollout-batch", type=int, default=8)
     ap.add_argument("--tf32-convs", action="store_true", help="let cuDNN use TF32 in the U-Net branch (reported separately)")
+    ap.add_argument("--no-cudnn-benchmark", action="store_true",
+                    help="do not let cuDNN autotune the conv algorithms of the U-Net branch (default: autotune on)")
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

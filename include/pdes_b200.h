@@ -87,6 +87,21 @@ int pdes_inv_w_gemm(const float* Z, const float* At, int lda, const float* x0, i
                     const float* bias, const float* res, const float* tables, int backward_scale,
                     float* out, float* pre, int B, int M, int H, int W, int m1, int m2, int act, void* stream);
 
+/* ---- K3b on the tensor cores (tcgen05 + TMEM, 3xTF32 split => fp32-faithful, rel. error ~2^-21 per product) -----
+ * Same contract as pdes_inv_w_gemm but the 1x1-conv weights come pre-packed by pdes_gemm_tc_pack (hi/lo TF32 split
+ * in the UMMA canonical K-major layout, one contiguous block per 16-channel chunk so it can be fetched with a bulk
+ * async copy).  Requires N <= 256 output channels.  `pdes_set_tensor_core_mode(1)` (default on sm_100a) makes the
+ * fused chains below use this kernel; mode 0 keeps every multiply on fp32 FFMA. */
+void pdes_set_tensor_core_mode(int mode);
+int pdes_get_tensor_core_mode(void);
+int pdes_gemm_tc_supported(int N, int K);
+int pdes_inv_w_gemm_tc_ok(int N, int K, int H, int W, int m2, const float* x0, const float* x1);
+size_t pdes_gemm_tc_pack_floats(int K, int N);
+int pdes_gemm_tc_pack(const float* Wt, int lda, int K, int N, float* packed, void* stream);
+int pdes_inv_w_gemm_tc(const float* Z, const float* wpack, const float* x0, int C0, const float* x1, int C1,
+                       const float* bias, const float* res, const float* tables, int backward_scale,
+                       float* out, float* pre, int B, int N, int H, int W, int m1, int m2, int act, void* stream);
+
 /* ---- pointwise / small helpers ------------------------------------------------------------------------
  * g_pre = g_out * act'(pre)  (GeluBackward of proc_ufno.py:118) */
 int pdes_act_bwd(const float* g_out, const float* pre, float* g_pre, size_t n, int act, void* stream);
@@ -98,6 +113,17 @@ int pdes_transpose(const float* in, float* out, int M, int K, void* stream);
 size_t pdes_wgrad_workspace_floats(int B, int M, int K, int HW);
 int pdes_wgrad(const float* g, const float* x0, int C0, const float* x1, int C1, float* dW, float* dbias,
                float* ws, int B, int M, int HW, void* stream);
+
+/* ---- U-Net branch helper: fused GroupNorm + activation ----------------------------------
+ * y = act(GroupNorm_G(x) * gamma + beta) and its backward (reference proc_unet_modern.py:234-245: norm -> activation
+ * in front of every 3x3 conv; :155,:194 before the final conv).  x, y: [B][C][HW]; stats [B*G][2] = (mean, rstd) is
+ * written by the forward and read by the backward; ws: pdes_gn_workspace_bytes() bytes (8-byte aligned). */
+size_t pdes_gn_workspace_bytes(int B, int C, int HW, int G);
+int pdes_gn_act_forward(const float* x, const float* gamma, const float* beta, float eps, float* y, float* stats,
+                        void* ws, int B, int C, int HW, int G, int act, void* stream);
+int pdes_gn_act_backward(const float* dy, const float* x, const float* gamma, const float* beta, const float* stats,
+                         float* dx, float* dgamma, float* dbeta, void* ws, int B, int C, int HW, int G, int act,
+                         void* stream);
 
 /* ---- fused chains (what the nn.Module binding calls) ----------------------------------------------------
  * One FNO_Layer / U-FNO block tail, forward:  K1 -> K2 -> K3a -> K3b.

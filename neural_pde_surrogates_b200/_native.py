@@ -33,10 +33,20 @@ _PROTOTYPES = {
     "pdes_mix_dw": (c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "pdes_inv_h": (c_int, [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
     "pdes_inv_w_gemm": (c_int, [_P, _P, _I, _P, _I, _P, _I, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "pdes_set_tensor_core_mode": (None, [_I]),
+    "pdes_get_tensor_core_mode": (c_int, []),
+    "pdes_gemm_tc_supported": (c_int, [_I, _I]),
+    "pdes_inv_w_gemm_tc_ok": (c_int, [_I, _I, _I, _I, _I, _P, _P]),
+    "pdes_gemm_tc_pack_floats": (c_size_t, [_I, _I]),
+    "pdes_gemm_tc_pack": (c_int, [_P, _I, _I, _I, _P, _P]),
+    "pdes_inv_w_gemm_tc": (c_int, [_P, _P, _P, _I, _P, _I, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "pdes_act_bwd": (c_int, [_P, _P, _P, c_size_t, _I, _P]),
     "pdes_transpose": (c_int, [_P, _P, _I, _I, _P]),
     "pdes_wgrad_workspace_floats": (c_size_t, [_I, _I, _I, _I]),
     "pdes_wgrad": (c_int, [_P, _P, _I, _P, _I, _P, _P, _P, _I, _I, _I, _P]),
+    "pdes_gn_workspace_bytes": (c_size_t, [_I, _I, _I, _I]),
+    "pdes_gn_act_forward": (c_int, [_P, _P, _P, ctypes.c_float, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "pdes_gn_act_backward": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "pdes_block_fwd_workspace_floats": (c_size_t, [_I, _I, _I, _I, _I, _I, _I]),
     "pdes_block_forward": (c_int, [_P, _I, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                                    _I, _I, _I, _I, _I, _I, _I, _P]),

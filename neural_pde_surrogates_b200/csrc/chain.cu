@@ -6,7 +6,7 @@
 namespace pdes {
 namespace {
 
-struct FwdWs { size_t P, Z, total; int nsplit; };
+struct FwdWs { size_t P, Z, PK, total; int nsplit; };
 FwdWs fwd_ws(int B, int Cin, int Cout, int H, int W, int m1, int m2) {
   (void)W;
   FwdWs w;
@@ -14,11 +14,12 @@ FwdWs fwd_ws(int B, int Cin, int Cout, int H, int W, int m1, int m2) {
   const size_t M2 = (size_t)2 * m1 * m2;
   w.P = 0;
   w.Z = w.P + round4((size_t)w.nsplit * B * Cout * M2 * 2);
-  w.total = w.Z + round4((size_t)B * H * 2 * m2 * Cout);
+  w.PK = w.Z + round4((size_t)B * H * 2 * m2 * Cout);
+  w.total = w.PK + round4(pdes_gemm_tc_pack_floats(Cin, Cout));      // packed 1x1 weights (tensor-core mode)
   return w;
 }
 
-struct BwdWs { size_t GO, PX, Zg, WG, total; int nsplit; };
+struct BwdWs { size_t GO, PX, Zg, WG, PK, total; int nsplit; };
 BwdWs bwd_ws(int B, int Cin, int C0, int Cout, int H, int W, int m1, int m2, bool has_conv) {
   BwdWs w;
   w.nsplit = pdes_mix_suggest_splits(B, Cout, C0, m1, m2);
@@ -27,7 +28,8 @@ BwdWs bwd_ws(int B, int Cin, int C0, int Cout, int H, int W, int m1, int m2, boo
   w.PX = w.GO + round4((size_t)B * Cout * M2 * 2);
   w.Zg = w.PX + round4((size_t)w.nsplit * B * C0 * M2 * 2);
   w.WG = w.Zg + round4((size_t)B * H * 2 * m2 * C0);
-  w.total = w.WG + (has_conv ? round4(pdes_wgrad_workspace_floats(B, Cout, Cin, H * W)) : 0);
+  w.PK = w.WG + (has_conv ? round4(pdes_wgrad_workspace_floats(B, Cout, Cin, H * W)) : 0);
+  w.total = w.PK + (has_conv ? round4(pdes_gemm_tc_pack_floats(Cout, C0)) : 0);
   return w;
 }
 
@@ -54,6 +56,11 @@ int pdes_block_forward(const float* h, int C0, const float* vb, int C1, const fl
   if (int e = pdes_dft_fwd(h, C0, vb, C1, B, H, W, m1, m2, tables, 0, Xsave, stream)) return e;
   if (int e = pdes_mix_fwd(Xsave, w1, w2, P, w.nsplit, B, Cin, Cout, H, m1, m2, stream)) return e;
   if (int e = pdes_inv_h(P, w.nsplit, B, Cout, H, m1, m2, tables, Z, stream)) return e;
+  if (wct != nullptr && pdes_get_tensor_core_mode() && pdes_inv_w_gemm_tc_ok(Cout, Cin, H, W, m2, h, vb)) {
+    float* PK = ws + w.PK;
+    if (int e = pdes_gemm_tc_pack(wct, Cout, Cin, Cout, PK, stream)) return e;
+    return pdes_inv_w_gemm_tc(Z, PK, h, C0, vb, C1, bias, res, tables, 0, out, pre, B, Cout, H, W, m1, m2, act, stream);
+  }
   return pdes_inv_w_gemm(Z, wct, Cout, h, C0, vb, C1, bias, res, tables, 0, out, pre, B, Cout, H, W, m1, m2, act,
                          stream);
 }
@@ -92,9 +99,16 @@ int pdes_block_backward(const float* g_out, const float* pre, const float* h, in
   if (int e = pdes_mix_dx(GO, w1, w2, PX, w.nsplit, B, Cin, Cout, C0, H, m1, m2, stream)) return e;
   // dh = Re(pruned inverse of GX, unit weights) + wc^T g_pre      (adjoint of K1 fused with the 1x1 dX)
   if (int e = pdes_inv_h(PX, w.nsplit, B, C0, H, m1, m2, tables, Zg, stream)) return e;
-  if (int e = pdes_inv_w_gemm(Zg, wc, Cin, has_conv ? gp : nullptr, Cout, nullptr, 0, nullptr, nullptr, tables, 1, dh,
-                              nullptr, B, C0, H, W, m1, m2, PDES_ACT_NONE, stream))
+  if (has_conv && pdes_get_tensor_core_mode() && pdes_inv_w_gemm_tc_ok(C0, Cout, H, W, m2, gp, nullptr)) {
+    float* PK = ws + w.PK;                     // At[k = o][n = i] = wc[o][i], lda = Cin
+    if (int e = pdes_gemm_tc_pack(wc, Cin, Cout, C0, PK, stream)) return e;
+    if (int e = pdes_inv_w_gemm_tc(Zg, PK, gp, Cout, nullptr, 0, nullptr, nullptr, tables, 1, dh, nullptr, B, C0, H, W,
+                                   m1, m2, PDES_ACT_NONE, stream))
+      return e;
+  } else if (int e = pdes_inv_w_gemm(Zg, wc, Cin, has_conv ? gp : nullptr, Cout, nullptr, 0, nullptr, nullptr, tables, 1,
+                                     dh, nullptr, B, C0, H, W, m1, m2, PDES_ACT_NONE, stream)) {
     return e;
+  }
   if (has_conv && (dwc != nullptr || dbias != nullptr)) {
     if (int e = pdes_wgrad(gp, h, C0, vb, C1, dwc, dbias, WG, B, Cout, H * W, stream)) return e;
   }

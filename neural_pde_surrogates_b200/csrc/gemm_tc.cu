@@ -1,0 +1,388 @@
+// K3b on the 5th-generation tensor cores (tcgen05 + TMEM), fp32-faithful via the 3xTF32 split.
+//
+//   pre[b][n][p] = sum_k xin[b][k][p] * Wt[k][n]  (+ spectral term + bias + residual),  out = act(pre)
+//
+// GEMM orientation: M = 128 pixels of one image (TMEM lanes), N = output channels (TMEM columns, <= 256),
+// K = input channels.  With pixels on the TMEM lanes every epilogue thread owns one pixel, so for a fixed channel a
+// warp stores 32 consecutive pixels: fully coalesced NCHW stores with no shared-memory transpose.
+//
+// fp32 parity: tcgen05 has no fp32 kind.  Every operand x is split as hi = tf32(x) (low 13 mantissa bits cleared) and
+// lo = x - hi (exact); D += A_hi*B_hi + A_lo*B_hi + A_hi*B_lo with fp32 accumulation in TMEM leaves a relative error
+// of ~2^-21 per product, well inside the 1e-5 budget (plain TF32 would be ~1e-3).  Tensor work triples, but
+// K3b is HBM-bound on the tensor pipe even at 3x (about 4 us of MMA per 128-pixel tile vs 6 us of HBM time).
+//
+// Operand staging (no swizzle, K-major canonical "core matrix" layout, 8 rows x 16 bytes):
+//   * A (activations): 128 producer threads, one pixel each, read 16 channels with warp-coalesced loads, split
+//     hi/lo in registers and write 16-byte rows of the core matrices (conflict-free) -- the split needs the data in
+//     registers anyway, so this is where the staging belongs;
+//   * B (weights): packed once per weight version by `k_pack_b_tf32` into per-chunk canonical blocks (hi, lo), so
+//     a chunk is ONE contiguous block fetched by a bulk async copy (TMA 1-D, SASS UBLKCP) that completes on the
+//     stage's mbarrier together with the producers' arrivals.
+// Pipeline: 2 stages of 16 channels; warp 4 lane 0 issues the MMAs and frees stages with tcgen05.commit; two CTAs
+// per SM (2 x 256 TMEM columns, 2 x ~82 KB shared memory) so one CTA's epilogue overlaps the other's main loop.
+#include "pdes_common.cuh"
+#include "pdes_ptx.cuh"
+
+namespace pdes {
+
+constexpr int kTcBK = 16;          // channels per pipeline stage
+constexpr int kTcM = 128;          // pixels per CTA tile
+constexpr int kTcMaxN = 256;
+
+__host__ __device__ inline int tc_npad(int N) { return (N + 15) & ~15; }
+__host__ __device__ inline int tc_nchunks(int K) { return (K + kTcBK - 1) / kTcBK; }
+// floats of one canonical block (N_pad x 16); a chunk is two blocks: hi then lo
+__host__ __device__ inline size_t tc_block_floats(int N) { return (size_t)tc_npad(N) * kTcBK; }
+
+namespace {
+
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+
+// Wt[k][n] (row stride lda) -> packed[chunk][hi|lo][canonical K-major block of N_pad rows x 16 k]
+__global__ void __launch_bounds__(256)
+k_pack_b_tf32(const float* __restrict__ Wt, int lda, int K, int N, int npad, int nchunks, float* __restrict__ out) {
+  const int total = nchunks * npad * kTcBK;
+  const int lbo_f = (npad / 8) * 32;                        // floats between K-adjacent core matrices
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int n = idx % npad;                               // n fastest: coalesced reads of Wt rows
+    const int kk = (idx / npad) % kTcBK;
+    const int c = idx / (npad * kTcBK);
+    const int k = c * kTcBK + kk;
+    const float w = (k < K && n < N) ? __ldg(Wt + (size_t)k * lda + n) : 0.0f;
+    const float hi = tf32_hi(w);
+    const size_t blk = (size_t)npad * kTcBK;
+    const size_t off = (size_t)(kk / 4) * lbo_f + (size_t)(n / 8) * 32 + (n % 8) * 4 + (kk % 4);
+    out[(size_t)c * 2 * blk + off] = hi;
+    out[(size_t)c * 2 * blk + blk + off] = w - hi;
+  }
+}
+
+#ifndef PDES_CPU_EMU
+
+struct TcParams {
+  const float* Z;       // [B][H][2*m2][N] or null
+  const float* wpack;   // packed weights
+  const float* x0; int C0;
+  const float* x1; int C1;
+  const float* bias;
+  const float* res;
+  const float* T;       // [2*m2][W]
+  float* out;
+  float* pre;
+  int N, npad, K, H, W, m2, act;
+};
+
+constexpr int kTcRaw = 3;          // depth of the raw activation ring fed by bulk async copies
+constexpr int kTcThreads = 192;    // warps 0-3: convert + epilogue, warp 4: MMA issue + TMEM, warp 5: bulk-copy issue
+
+// Pipeline of one CTA (= 128 pixels x all output channels of one image):
+//   warp 5 lane 0 : raw activations, 16 channel rows of 512 B per chunk, bulk async copies into a 3-deep ring
+//   warps 0-3     : ring -> registers -> hi/lo TF32 split -> canonical K-major A tile (2 stages); thread 0 also
+//                   launches the bulk copy of the pre-packed weight chunk into the same stage
+//   warp 4 lane 0 : 3 x tcgen05.mma per K=8 step into TMEM, tcgen05.commit frees the stage
+//   spectral term : appended as extra K chunks: A = T[j][w] masked by the pixel's row, B = Z[b][row][j][:]
+//   warps 0-3     : epilogue, thread = pixel = TMEM lane; residual prefetched one 32-column group ahead
+__global__ void __launch_bounds__(kTcThreads, 2)
+k_inv_w_gemm_tc(TcParams p) {
+  PDES_DYN_SMEM(unsigned char, smem_raw);
+  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int npad = p.npad;
+  const uint32_t a_blk = kTcM * kTcBK * 4;                 // 8 KB
+  const uint32_t b_blk = (uint32_t)npad * kTcBK * 4;
+  const uint32_t stage_bytes = 2 * a_blk + 2 * b_blk;
+  float* raw = reinterpret_cast<float*>(base + 2 * (size_t)stage_bytes);      // [kTcRaw][16][128]
+  __shared__ __align__(8) unsigned long long full_bar[2], empty_bar[2], raw_full[kTcRaw], raw_empty[kTcRaw], done_bar;
+  __shared__ uint32_t tmem_slot;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int HW = p.H * p.W, W = p.W;
+  const int p0 = blockIdx.x * kTcM, b = blockIdx.y;
+  const int nx = tc_nchunks(p.K);
+  const int J = 2 * p.m2;
+  const int plast = (p0 + kTcM - 1 < HW - 1) ? (p0 + kTcM - 1) : (HW - 1);
+  const int h0 = p0 / W;
+  const int kspec = (p.Z != nullptr) ? (plast / W - h0 + 1) * J : 0;
+  const int nsp = tc_nchunks(kspec);
+  const int nchunks = nx + nsp;
+  const int npx = (HW - p0 < kTcM) ? (HW - p0) : kTcM;
+  const uint32_t tmem_cols = npad <= 32 ? 32 : (npad <= 64 ? 64 : (npad <= 128 ? 128 : 256));
+
+  if (tid == 0) {
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(&full_bar[s], 129);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < kTcRaw; ++s) {
+      ptx::mbar_init(&raw_full[s], 1);
+      ptx::mbar_init(&raw_empty[s], 128);
+    }
+    ptx::mbar_init(&done_bar, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 4) {
+    ptx::tmem_alloc(&tmem_slot, tmem_cols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp < 4) {
+    // ------------------------------------------------------------------ convert: one pixel per thread
+    const int pp = p0 + tid;
+    const bool pvalid = pp < HW;
+    const int hh = pvalid ? pp / W : 0, ww = pvalid ? pp % W : 0;
+    const uint32_t row_off = (uint32_t)(tid >> 3) * 128 + (uint32_t)(tid & 7) * 16;   // (m/8)*SBO + (m%8)*16
+    const uint32_t lbo_b = (uint32_t)(npad / 8) * 128;
+    for (int c = 0; c < nchunks; ++c) {
+      const int s = c & 1, u = c >> 1;
+      if (c >= 2) ptx::mbar_wait(&empty_bar[s], (uint32_t)((u - 1) & 1));
+      unsigned char* st = base + (size_t)s * stage_bytes;
+      float v[kTcBK];
+      if (c >= nsp) {
+        const int cx = c - nsp;                               // activation chunk index
+        if (tid == 0) {
+          ptx::mbar_arrive_expect_tx(&full_bar[s], 2 * b_blk);
+          ptx::bulk_g2s(st + 2 * a_blk, p.wpack + (size_t)cx * 2 * (b_blk / 4), 2 * b_blk, &full_bar[s]);
+        }
+        const int slot = cx % kTcRaw;
+        ptx::mbar_wait(&raw_full[slot], (uint32_t)((cx / kTcRaw) & 1));
+        const float* rw = raw + (size_t)slot * kTcBK * kTcM + tid;
+#pragma unroll
+        for (int kk = 0; kk < kTcBK; ++kk) v[kk] = (pvalid && cx * kTcBK + kk < p.K) ? rw[kk * kTcM] : 0.0f;
+        ptx::mbar_arrive(&raw_empty[slot]);
+      } else {
+        const int cs = c;                                     // spectral chunks come first: their L2 latency
+                                                              // overlaps the first bulk copies of the activations
+        if (tid == 0) ptx::mbar_arrive(&full_bar[s]);          // stands in for the weight copy's arrival
+        // A: T[j][w] if this pixel sits in row h0 + r, else 0   (block-diagonal over the rows of the tile)
+#pragma unroll
+        for (int kk = 0; kk < kTcBK; ++kk) {
+          const int k = cs * kTcBK + kk;
+          const int r = k / J, j = k - r * J;
+          v[kk] = (pvalid && k < kspec && hh - h0 == r) ? __ldg(p.T + (size_t)j * W + ww) : 0.0f;
+        }
+        // B: Z[b][h0 + r][j][n] -> canonical (n, kk); 8 independent loads in flight per thread
+        constexpr int UN = 8;
+        const int nelem = npad * kTcBK;
+        for (int base0 = tid; base0 < nelem; base0 += 128 * UN) {
+          float z[UN];
+#pragma unroll
+          for (int uu = 0; uu < UN; ++uu) {
+            const int idx = base0 + uu * 128;
+            const int kk = idx / npad, n = idx - kk * npad;
+            const int k = cs * kTcBK + kk;
+            const int r = k / J, j = k - r * J;
+            z[uu] = (idx < nelem && k < kspec && n < p.N)
+                        ? __ldg(p.Z + (((size_t)b * p.H + h0 + r) * J + j) * p.N + n) : 0.0f;
+          }
+#pragma unroll
+          for (int uu = 0; uu < UN; ++uu) {
+            const int idx = base0 + uu * 128;
+            if (idx < nelem) {
+              const int kk = idx / npad, n = idx - kk * npad;
+              const float zh = tf32_hi(z[uu]);
+              const uint32_t off = (uint32_t)(kk >> 2) * lbo_b + (uint32_t)(n >> 3) * 128 + (uint32_t)(n & 7) * 16 + (uint32_t)(kk & 3) * 4;
+              *reinterpret_cast<float*>(st + 2 * a_blk + off) = zh;
+              *reinterpret_cast<float*>(st + 2 * a_blk + b_blk + off) = z[uu] - zh;
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < kTcBK / 4; ++q) {
+        float4 hi, lo;
+        hi.x = tf32_hi(v[4 * q + 0]); lo.x = v[4 * q + 0] - hi.x;
+        hi.y = tf32_hi(v[4 * q + 1]); lo.y = v[4 * q + 1] - hi.y;
+        hi.z = tf32_hi(v[4 * q + 2]); lo.z = v[4 * q + 2] - hi.z;
+        hi.w = tf32_hi(v[4 * q + 3]); lo.w = v[4 * q + 3] - hi.w;
+        const uint32_t off = (uint32_t)q * (kTcM / 8) * 128 + row_off;                // (k/4)*LBO_A + row
+        *reinterpret_cast<float4*>(st + off) = hi;
+        *reinterpret_cast<float4*>(st + a_blk + off) = lo;
+      }
+      ptx::fence_proxy_async();
+      ptx::mbar_arrive(&full_bar[s]);
+    }
+
+    // ------------------------------------------------------------------ epilogue: thread = pixel (TMEM lane)
+    const int N = p.N;
+    const size_t obase = (size_t)b * N * HW + pp;
+    auto load_res = [&](float (&rr)[32], int n0) {
+#pragma unroll
+      for (int e = 0; e < 32; ++e) {
+        const int n = n0 + e;
+        rr[e] = (p.res != nullptr && pvalid && n < N) ? __ldg(p.res + obase + (size_t)n * HW) : 0.0f;
+      }
+    };
+    auto finish = [&](const float (&rr)[32], int n0) {
+      uint32_t r[32];
+      ptx::tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)n0, r);
+      ptx::tmem_ld_wait();
+      if (!pvalid) return;
+#pragma unroll
+      for (int e = 0; e < 32; ++e) {
+        const int n = n0 + e;
+        if (n < N) {
+          float v = __uint_as_float(r[e]) + rr[e];
+          if (p.bias != nullptr) v += __ldg(p.bias + n);
+          if (p.pre != nullptr) p.pre[obase + (size_t)n * HW] = v;
+          if (p.act == PDES_ACT_GELU) v = gelu_f(v);
+          p.out[obase + (size_t)n * HW] = v;
+        }
+      }
+    };
+    float ra[32], rb[32];
+    load_res(ra, 0);                                   // issued before the accumulator is complete
+    ptx::mbar_wait(&done_bar, 0);
+    ptx::tc_fence_after();
+    for (int n0 = 0; n0 < npad; n0 += 64) {
+      const bool second = n0 + 32 < npad;
+      if (second) load_res(rb, n0 + 32);
+      finish(ra, n0);
+      if (second) {
+        if (n0 + 64 < npad) load_res(ra, n0 + 64);
+        finish(rb, n0 + 32);
+      }
+    }
+    ptx::tc_fence_before();
+  } else if (warp == 4) {
+    if (lane == 0) {
+      // ---------------------------------------------------------------- MMA issuer (one thread)
+      const uint32_t idesc = ptx::idesc_tf32(kTcM, npad);
+      const uint32_t lbo_a = (kTcM / 8) * 128, lbo_b = (uint32_t)(npad / 8) * 128, sbo = 128;
+      for (int c = 0; c < nchunks; ++c) {
+        const int s = c & 1, u = c >> 1;
+        ptx::mbar_wait(&full_bar[s], (uint32_t)(u & 1));
+        ptx::tc_fence_after();
+        const uint32_t sa = ptx::smem_u32(base + (size_t)s * stage_bytes);
+        const uint32_t sb = sa + 2 * a_blk;
+#pragma unroll
+        for (int ks = 0; ks < kTcBK / 8; ++ks) {
+          const uint64_t a_hi = ptx::smem_desc_noswizzle(sa + ks * 2 * lbo_a, lbo_a, sbo);
+          const uint64_t a_lo = ptx::smem_desc_noswizzle(sa + a_blk + ks * 2 * lbo_a, lbo_a, sbo);
+          const uint64_t b_hi = ptx::smem_desc_noswizzle(sb + ks * 2 * lbo_b, lbo_b, sbo);
+          const uint64_t b_lo = ptx::smem_desc_noswizzle(sb + b_blk + ks * 2 * lbo_b, lbo_b, sbo);
+          ptx::mma_tf32(tmem_base, a_lo, b_hi, idesc, (c | ks) != 0 ? 1u : 0u);   // small terms first
+          ptx::mma_tf32(tmem_base, a_hi, b_lo, idesc, 1u);
+          ptx::mma_tf32(tmem_base, a_hi, b_hi, idesc, 1u);
+        }
+        ptx::tc_commit(&empty_bar[s]);
+      }
+      ptx::tc_commit(&done_bar);
+    }
+  } else if (lane == 0) {
+    // ------------------------------------------------------------------ bulk-copy issuer (raw activation rows)
+    const uint32_t rowbytes = (uint32_t)npx * 4;
+    for (int c = 0; c < nx; ++c) {
+      const int slot = c % kTcRaw, use = c / kTcRaw;
+      if (c >= kTcRaw) ptx::mbar_wait(&raw_empty[slot], (uint32_t)((use - 1) & 1));
+      const int nk = (p.K - c * kTcBK < kTcBK) ? (p.K - c * kTcBK) : kTcBK;
+      ptx::mbar_arrive_expect_tx(&raw_full[slot], (uint32_t)nk * rowbytes);
+      float* dst = raw + (size_t)slot * kTcBK * kTcM;
+      for (int kk = 0; kk < nk; ++kk) {
+        const int k = c * kTcBK + kk;
+        const float* src = (k < p.C0) ? p.x0 + ((size_t)b * p.C0 + k) * HW : p.x1 + ((size_t)b * p.C1 + (k - p.C0)) * HW;
+        ptx::bulk_g2s(dst + kk * kTcM, src + p0, rowbytes, &raw_full[slot]);
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 4) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+#endif  // !PDES_CPU_EMU
+
+int g_tc_mode =
+#ifdef PDES_CPU_EMU
+    0;
+#else
+    1;
+#endif
+
+}  // namespace
+}  // namespace pdes
+
+extern "C" {
+
+void pdes_set_tensor_core_mode(int mode) {
+#ifdef PDES_CPU_EMU
+  (void)mode;
+  pdes::g_tc_mode = 0;
+#else
+  pdes::g_tc_mode = mode ? 1 : 0;
+#endif
+}
+
+int pdes_get_tensor_core_mode(void) { return pdes::g_tc_mode; }
+
+int pdes_gemm_tc_supported(int N, int K) { return (N >= 1 && N <= pdes::kTcMaxN && K >= 1) ? 1 : 0; }
+
+/* The tensor-core kernel streams activation rows with 16-byte-granular bulk copies: needs H*W % 4 == 0 and 16-byte
+ * aligned activation pointers; the spectral term is folded in as (rows per 128-pixel tile) * 2*m2 extra K steps, so
+ * very narrow grids (many rows per tile) stay on the FFMA kernel. */
+int pdes_inv_w_gemm_tc_ok(int N, int K, int H, int W, int m2, const float* x0, const float* x1) {
+  if (!pdes_gemm_tc_supported(N, K)) return 0;
+  if ((H * W) % 4 != 0) return 0;
+  if ((reinterpret_cast<uintptr_t>(x0) & 15u) != 0 || (x1 != nullptr && (reinterpret_cast<uintptr_t>(x1) & 15u) != 0)) return 0;
+  const int rows = (pdes::kTcM + W - 1) / W + 1;
+  if (m2 > 0 && rows * 2 * m2 > 8 * pdes::kTcBK) return 0;
+  return 1;
+}
+
+size_t pdes_gemm_tc_pack_floats(int K, int N) {
+  if (!pdes_gemm_tc_supported(N, K)) return 0;
+  return (size_t)pdes::tc_nchunks(K) * 2 * pdes::tc_block_floats(N);
+}
+
+int pdes_gemm_tc_pack(const float* Wt, int lda, int K, int N, float* packed, void* stream) {
+  using namespace pdes;
+  PDES_REQUIRE(Wt && packed && K > 0 && N > 0 && lda >= N, PDES_ERR_ARG, "pdes_gemm_tc_pack: bad arguments");
+  PDES_REQUIRE(pdes_gemm_tc_supported(N, K), PDES_ERR_UNSUPPORTED, "pdes_gemm_tc_pack: N=%d > %d", N, kTcMaxN);
+  const int npad = tc_npad(N), nchunks = tc_nchunks(K);
+  const int total = nchunks * npad * kTcBK;
+  auto kfn = k_pack_b_tf32;
+  PDES_LAUNCH(kfn, dim3((unsigned)ceil_div(total, 256)), dim3(256), 0, stream, Wt, lda, K, N, npad, nchunks, packed);
+  return check_launch("pdes_gemm_tc_pack");
+}
+
+int pdes_inv_w_gemm_tc(const float* Z, const float* wpack, const float* x0, int C0, const float* x1, int C1,
+                       const float* bias, const float* res, const float* tables, int backward_scale, float* out,
+                       float* pre, int B, int N, int H, int W, int m1, int m2, int act, void* stream) {
+  using namespace pdes;
+#ifdef PDES_CPU_EMU
+  (void)Z; (void)wpack; (void)x0; (void)C0; (void)x1; (void)C1; (void)bias; (void)res; (void)tables;
+  (void)backward_scale; (void)out; (void)pre; (void)B; (void)N; (void)H; (void)W; (void)m1; (void)m2; (void)act;
+  (void)stream;
+  set_error("pdes_inv_w_gemm_tc: tcgen05 path is not available in the CPU emulation build");
+  return PDES_ERR_UNSUPPORTED;
+#else
+  PDES_REQUIRE(wpack && x0 && out, PDES_ERR_ARG, "pdes_inv_w_gemm_tc: null pointer");
+  PDES_REQUIRE(B > 0 && N > 0 && H > 0 && W > 0 && C0 > 0 && C1 >= 0, PDES_ERR_ARG, "pdes_inv_w_gemm_tc: bad sizes");
+  PDES_REQUIRE((C1 == 0) == (x1 == nullptr), PDES_ERR_ARG, "pdes_inv_w_gemm_tc: x1/C1 mismatch");
+  PDES_REQUIRE(pdes_inv_w_gemm_tc_ok(N, C0 + C1, H, W, Z != nullptr ? m2 : 0, x0, x1), PDES_ERR_UNSUPPORTED,
+               "pdes_inv_w_gemm_tc: shape/alignment not supported by the tensor-core kernel (N=%d, HW=%d, W=%d)", N, H * W, W);
+  PDES_REQUIRE(B <= 65535, PDES_ERR_UNSUPPORTED, "pdes_inv_w_gemm_tc: grid too large");
+  PDES_REQUIRE(act == PDES_ACT_NONE || act == PDES_ACT_GELU, PDES_ERR_ARG, "pdes_inv_w_gemm_tc: unknown activation");
+  PDES_REQUIRE((reinterpret_cast<uintptr_t>(wpack) & 15u) == 0, PDES_ERR_ARG, "pdes_inv_w_gemm_tc: wpack must be 16-byte aligned");
+  TcParams p;
+  p.Z = Z; p.wpack = wpack; p.x0 = x0; p.C0 = C0; p.x1 = x1; p.C1 = C1; p.bias = bias; p.res = res; p.T = nullptr;
+  if (Z != nullptr) {
+    PDES_REQUIRE(tables != nullptr && m1 > 0 && m2 > 0 && m2 <= W / 2 + 1, PDES_ERR_ARG, "pdes_inv_w_gemm_tc: spectral term needs tables/modes");
+    const TableLayout t = table_layout(H, W, m1, m2);
+    p.T = tables + (backward_scale ? t.tinv_b : t.tinv_f);
+  }
+  p.out = out; p.pre = pre; p.N = N; p.npad = tc_npad(N); p.K = C0 + C1; p.H = H; p.W = W; p.m2 = m2; p.act = act;
+  const size_t stage = (size_t)2 * kTcM * kTcBK * 4 + (size_t)2 * p.npad * kTcBK * 4;
+  const size_t smem = 2 * stage + (size_t)kTcRaw * kTcBK * kTcM * 4 + 1024;
+  auto kfn = k_inv_w_gemm_tc;
+  PDES_SET_SMEM(kfn, smem);
+  PDES_LAUNCH(kfn, dim3((unsigned)ceil_div(H * W, kTcM), (unsigned)B), dim3(kTcThreads), smem, stream, p);
+  return check_launch("pdes_inv_w_gemm_tc");
+#endif
+}
+
+}  // extern "C"

@@ -82,6 +82,8 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, F body) {
 
 static inline void __syncthreads() { pthread_barrier_wait(&pdes_emu::g_barrier); }
 template <class T> static inline T __ldg(const T* p) { return *p; }
+static inline unsigned __float_as_uint(float f) { unsigned u; std::memcpy(&u, &f, 4); return u; }
+static inline float __uint_as_float(unsigned u) { float f; std::memcpy(&f, &u, 4); return f; }
 static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 static inline const char* cudaGetErrorString(cudaError_t) { return "emu"; }
 

@@ -36,9 +36,11 @@ __device__ __forceinline__ bool mbar_try_wait(void* bar, uint32_t parity) {
 }
 // Bounded wait: a protocol bug must fault (trap) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(void* bar, uint32_t parity) {
-  for (uint32_t it = 0; it < (1u << 26); ++it)
-    if (mbar_try_wait(bar, parity)) return;
-  __trap();
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) __trap();      // ~2 s at 2 GHz: fault loudly, never hang
+  }
 }
 
 // 1-D bulk async copy global -> shared, completion counted in bytes on an mbarrier (src/dst/size 16-byte aligned)

@@ -214,3 +214,56 @@ def act_code(module) -> int | None:
     if isinstance(module, torch.nn.Identity):
         return ACT_NONE
     return None
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# U-Net branch helper: fused GroupNorm + activation (csrc/groupnorm.cu)
+class GroupNormActFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, groups, eps, act):
+        lib = _lib()
+        _check_f32_cuda("x", x)
+        x = x.contiguous()
+        B, C = x.shape[0], x.shape[1]
+        HW = x.numel() // (B * C)
+        dev = x.device
+        with torch.cuda.device(dev):
+            y = torch.empty_like(x)
+            stats = torch.empty(B * groups * 2, dtype=torch.float32, device=dev)
+            ws = torch.empty((lib.pdes_gn_workspace_bytes(B, C, HW, groups) + 7) // 8, dtype=torch.float64, device=dev)
+            p = lambda t: None if t is None else t.data_ptr()
+            _native.check(lib, lib.pdes_gn_act_forward(p(x), p(weight), p(bias), float(eps), p(y), p(stats), p(ws),
+                                                       B, C, HW, groups, act, _stream()))
+            _counters["launches"] += 3
+        ctx.save_for_backward(x, weight, bias, stats)
+        ctx.groups, ctx.act = groups, act
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _lib()
+        x, weight, bias, stats = ctx.saved_tensors
+        dy = dy.contiguous()
+        B, C = x.shape[0], x.shape[1]
+        HW = x.numel() // (B * C)
+        dev = x.device
+        with torch.cuda.device(dev):
+            dx = torch.empty_like(x)
+            dw = torch.empty_like(weight) if weight is not None else None
+            db = torch.empty_like(bias) if bias is not None else None
+            ws = torch.empty((lib.pdes_gn_workspace_bytes(B, C, HW, ctx.groups) + 7) // 8, dtype=torch.float64, device=dev)
+            p = lambda t: None if t is None else t.data_ptr()
+            _native.check(lib, lib.pdes_gn_act_backward(p(dy), p(x), p(weight), p(bias), p(stats), p(dx), p(dw), p(db),
+                                                        p(ws), B, C, HW, ctx.groups, ctx.act, _stream()))
+            _counters["launches"] += 3
+        return dx, dw, db, None, None, None
+
+
+def group_norm_act(x, norm, act):
+    """act(norm(x)) for an nn.GroupNorm `norm` (or Identity) -- one fused kernel pair on CUDA, plain PyTorch otherwise
+    (the U-Net branch is a PyTorch component; only its GroupNorm+GELU is replaced on the GPU)."""
+    code = act_code(act)
+    if isinstance(norm, torch.nn.GroupNorm) and x.is_cuda and x.dtype == torch.float32 and code is not None:
+        return GroupNormActFunction.apply(x, norm.weight, norm.bias, norm.num_groups, norm.eps, code)
+    y = norm(x)
+    return y if act is None else act(y)

@@ -19,6 +19,7 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
+from . import ops
 from .interfaces import D, M
 
 
@@ -69,8 +70,8 @@ class ResidualBlock(nn.Module):
         self.norm2 = nn.GroupNorm(n_groups, out_channels) if norm else nn.Identity()
 
     def forward(self, x):
-        y = self.conv1(self.activation(self.norm1(x)))
-        y = self.conv2(self.activation(self.norm2(y)))
+        y = self.conv1(ops.group_norm_act(x, self.norm1, self.activation))
+        y = self.conv2(ops.group_norm_act(y, self.norm2, self.activation))
         skip = self.shortcut(x)
         return fit_to(y, skip.shape[-2:]) + skip
 
@@ -242,4 +243,4 @@ class UNetModern(nn.Module):
             if c is not None:
                 parts.append(fit_to(c, here))
             h = m(torch.cat(parts, dim=1))
-        return fit_to(self.final(self.activation(self.norm(h))), target)
+        return fit_to(self.final(ops.group_norm_act(h, self.norm, self.activation)), target)

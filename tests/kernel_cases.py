@@ -233,3 +233,106 @@ def check_block(be, shape, act=1, use_res=True, use_conv=True, reference_init=Fa
     for k, v in errs.items():
         assert v < tol, f"block {k} {shape} act={act} res={use_res} conv={use_conv}: rel L2 {v:.3e}"
     return errs
+
+
+def check_tc_pack(be, K=21, N=12, lda=14):
+    """pdes_gemm_tc_pack: hi/lo TF32 split written in the UMMA canonical K-major layout (8 rows x 16 bytes core
+    matrices, no swizzle), one (hi, lo) block pair per 16-channel chunk."""
+    rng = _rng(11)
+    Wt = rng.standard_normal((K, lda)).astype(np.float32)
+    n_f = be.lib.pdes_gemm_tc_pack_floats(K, N)
+    npad, nch = (N + 15) // 16 * 16, (K + 15) // 16
+    assert n_f == nch * 2 * npad * 16
+    out = be.empty((n_f,))
+    dWt = be.upload(Wt)                       # keep the buffer alive across the call
+    be.check(be.lib.pdes_gemm_tc_pack(be.ptr(dWt), lda, K, N, be.ptr(out), be.stream))
+    got = be.download(out).reshape(nch, 2, npad * 16)
+    hi_ref = (Wt.view(np.uint32) & np.uint32(0xffffe000)).view(np.float32)
+    lbo = (npad // 8) * 32
+    for c in range(nch):
+        for kk in range(16):
+            for n in range(npad):
+                k = c * 16 + kk
+                off = (kk // 4) * lbo + (n // 8) * 32 + (n % 8) * 4 + (kk % 4)
+                w = Wt[k, n] if (k < K and n < N) else np.float32(0)
+                h = hi_ref[k, n] if (k < K and n < N) else np.float32(0)
+                assert got[c, 0, off] == h and got[c, 1, off] == np.float32(w - h), (c, kk, n)
+    # hi + lo reconstructs the weight exactly and lo is below 2^-10 |w|
+    assert np.all(np.abs(got[:, 1]) <= np.abs(got[:, 0]) * 2.0 ** -10 + 1e-30)
+
+
+def check_inverse_tc(be, shape, act=1, backward_scale=0, with_spectral=True):
+    """tcgen05 K3b (3xTF32) against the float64 oracle; same inputs as check_inverse."""
+    B, C0, C1, Cout, H, W, m1, m2 = shape
+    Cin = C0 + C1
+    rng = _rng(3)
+    nsplit = 2
+    P = (rng.standard_normal((nsplit, B, Cout, 2 * m1, m2)) + 1j * rng.standard_normal((nsplit, B, Cout, 2 * m1, m2))).astype(np.complex64)
+    x0 = rng.standard_normal((B, C0, H, W)).astype(np.float32)
+    x1 = rng.standard_normal((B, C1, H, W)).astype(np.float32) if C1 else None
+    wc = (rng.standard_normal((Cout, Cin)) / np.sqrt(Cin)).astype(np.float32)
+    bias = rng.standard_normal(Cout).astype(np.float32)
+    res = rng.standard_normal((B, Cout, H, W)).astype(np.float32)
+    tab = be.tables(H, W, m1, m2)
+    dP = be.upload(P)
+    Z = be.empty((B, H, 2 * m2, Cout))
+    be.check(be.lib.pdes_inv_h(be.ptr(dP), nsplit, B, Cout, H, m1, m2, be.ptr(tab), be.ptr(Z), be.stream))
+    wct = be.upload(np.ascontiguousarray(wc.T))
+    pack = be.empty((be.lib.pdes_gemm_tc_pack_floats(Cin, Cout),))
+    be.check(be.lib.pdes_gemm_tc_pack(be.ptr(wct), Cout, Cin, Cout, be.ptr(pack), be.stream))
+    dx0, dx1 = be.upload(x0), (be.upload(x1) if C1 else None)
+    if not be.lib.pdes_inv_w_gemm_tc_ok(Cout, Cin, H, W, m2 if with_spectral else 0, be.ptr(dx0), be.ptr(dx1)):
+        return None                     # shape stays on the FFMA kernel (odd H*W, or too many rows per 128-pixel tile)
+    dbias, dres = be.upload(bias), be.upload(res)
+    out = be.empty((B, Cout, H, W))
+    pre = be.empty((B, Cout, H, W))
+    be.check(be.lib.pdes_inv_w_gemm_tc(be.ptr(Z) if with_spectral else None, be.ptr(pack), be.ptr(dx0), C0, be.ptr(dx1), C1,
+                                       be.ptr(dbias), be.ptr(dres), be.ptr(tab), backward_scale, be.ptr(out), be.ptr(pre),
+                                       B, Cout, H, W, m1, m2, act, be.stream))
+    xin = x0 if x1 is None else np.concatenate([x0, x1], axis=1)
+    ref = np.einsum("oi,bihw->bohw", wc.astype(np.float64), xin) + bias[None, :, None, None] + res
+    if with_spectral:
+        lscale = np.ones(m2) if backward_scale else so.hermitian_scale(H, W, m2)
+        ref = ref + so.inv_pruned(P.astype(np.complex128).sum(axis=0), H, W, lscale)
+    e_pre = so.rel_l2(be.download(pre), ref)
+    e_out = so.rel_l2(be.download(out), so.gelu(ref) if act == 1 else ref)
+    assert e_pre < TOL and e_out < TOL, f"tc inverse {shape}: pre {e_pre:.3e} out {e_out:.3e}"
+    return e_pre, e_out
+
+
+def check_groupnorm(be, B=3, C=12, HW=35, G=4, act=1):
+    """Fused GroupNorm + GELU forward/backward against a float64 numpy restatement."""
+    rng = _rng(21)
+    x = (rng.standard_normal((B, C, HW)) * 1.7 + 0.4).astype(np.float32)
+    dy = rng.standard_normal((B, C, HW)).astype(np.float32)
+    gamma = (1 + 0.3 * rng.standard_normal(C)).astype(np.float32)
+    beta = (0.2 * rng.standard_normal(C)).astype(np.float32)
+    eps = 1e-5
+    import ctypes
+    dx_, dy_, dg_, db_ = be.upload(x), be.upload(dy), be.upload(gamma), be.upload(beta)
+    y = be.empty((B, C, HW)); stats = be.empty((B * G * 2,))
+    nws = (be.lib.pdes_gn_workspace_bytes(B, C, HW, G) + 3) // 4
+    ws = be.empty((nws + 2,))
+    wsp = (be.ptr(ws) + 7) // 8 * 8
+    be.check(be.lib.pdes_gn_act_forward(be.ptr(dx_), be.ptr(dg_), be.ptr(db_), ctypes.c_float(eps), be.ptr(y), be.ptr(stats),
+                                        wsp, B, C, HW, G, act, be.stream))
+    gx = be.empty((B, C, HW)); gg = be.empty((C,)); gb = be.empty((C,))
+    be.check(be.lib.pdes_gn_act_backward(be.ptr(dy_), be.ptr(dx_), be.ptr(dg_), be.ptr(db_), be.ptr(stats), be.ptr(gx),
+                                         be.ptr(gg), be.ptr(gb), wsp, B, C, HW, G, act, be.stream))
+    xd = x.astype(np.float64).reshape(B, G, -1)
+    mean = xd.mean(axis=2, keepdims=True); var = xd.var(axis=2, keepdims=True)
+    rstd = 1.0 / np.sqrt(var + eps)
+    xh = ((xd - mean) * rstd).reshape(B, C, HW)
+    z = xh * gamma[None, :, None] + beta[None, :, None]
+    yr = so.gelu(z) if act else z
+    dz = dy.astype(np.float64) * (so.gelu_grad(z) if act else 1.0)
+    dgam = (dz * xh).sum(axis=(0, 2)); dbet = dz.sum(axis=(0, 2))
+    gdz = (dz * gamma[None, :, None]).reshape(B, G, -1)
+    xhg = xh.reshape(B, G, -1)
+    m1 = gdz.mean(axis=2, keepdims=True); m2 = (gdz * xhg).mean(axis=2, keepdims=True)
+    dxr = (rstd * (gdz - m1 - xhg * m2)).reshape(B, C, HW)
+    errs = dict(y=so.rel_l2(be.download(y), yr), dx=so.rel_l2(be.download(gx), dxr),
+                dgamma=so.rel_l2(be.download(gg), dgam), dbeta=so.rel_l2(be.download(gb), dbet))
+    for k, v in errs.items():
+        assert v < TOL, f"groupnorm {k}: {v:.3e}"
+    return errs

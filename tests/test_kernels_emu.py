@@ -62,3 +62,15 @@ def test_bad_arguments_raise(be):
         be.check(lib.pdes_dft_fwd(None, 1, None, 0, 1, 8, 8, 2, 2, be.ptr(tab), 0, be.ptr(X), be.stream))
     with pytest.raises(ValueError):
         be.check(lib.pdes_tables_fill(8, 8, 9, 2, x.ctypes.data))
+
+
+def test_tc_weight_pack_layout(be):
+    kc.check_tc_pack(be)
+    kc.check_tc_pack(be, K=16, N=16, lda=16)
+    assert be.lib.pdes_get_tensor_core_mode() == 0          # the emulation build never takes the tcgen05 path
+
+
+def test_groupnorm_act(be):
+    kc.check_groupnorm(be, B=3, C=12, HW=35, G=4, act=1)       # scalar path
+    kc.check_groupnorm(be, B=2, C=10, HW=64, G=1, act=1)       # GroupNorm(1, C) as in the residual blocks, vector path
+    kc.check_groupnorm(be, B=2, C=8, HW=16, G=8, act=0)

@@ -64,3 +64,46 @@ def test_block_reference_init_full_shape(be):
 def test_large_grid(be):
     """BASELINE config 5 shape class: 256x256 grid, 32x32 modes (exercises the chunked shared-memory paths)."""
     kc.check_block(be, (1, 16, 1, 16, 256, 256, 32, 32))
+
+
+# ---- tcgen05 / TMEM path (3xTF32) ---------------------------------------------------------------------------
+@pytest.fixture(params=[1, 0], ids=["tc", "ffma"])
+def tc_mode(request, be):
+    be.lib.pdes_set_tensor_core_mode(request.param)
+    yield request.param
+    be.lib.pdes_set_tensor_core_mode(1)
+
+
+def test_tc_weight_pack_layout(be):
+    kc.check_tc_pack(be)
+    kc.check_tc_pack(be, K=193, N=192, lda=192)
+
+
+TC_SHAPES = kc.SMALL_SHAPES + FULL_SHAPES + [(2, 20, 1, 24, 10, 24, 3, 4), (1, 40, 0, 200, 16, 32, 5, 7)]
+
+
+@pytest.mark.parametrize("shape", TC_SHAPES)
+def test_tc_inverse_gemm(be, shape):
+    kc.check_inverse_tc(be, shape)
+
+
+def test_tc_path_is_taken_for_config_shapes(be):
+    for shape in FULL_SHAPES + TC_SHAPES[-2:]:
+        assert kc.check_inverse_tc(be, shape) is not None
+
+
+def test_tc_gemm_only_and_backward_scale(be):
+    kc.check_inverse_tc(be, kc.SMALL_SHAPES[2], act=0, with_spectral=False)
+    kc.check_inverse_tc(be, kc.SMALL_SHAPES[5], act=0, backward_scale=1)
+
+
+@pytest.mark.parametrize("shape", [kc.SMALL_SHAPES[3], kc.SMALL_SHAPES[6], FULL_SHAPES[0]])
+def test_block_both_modes(be, shape, tc_mode):
+    assert be.lib.pdes_get_tensor_core_mode() == tc_mode
+    kc.check_block(be, shape, act=1, use_res=True, use_conv=True)
+
+
+def test_groupnorm_act(be):
+    kc.check_groupnorm(be, B=3, C=12, HW=35, G=4, act=1)
+    kc.check_groupnorm(be, B=2, C=193, HW=96 * 64, G=1, act=1)     # the U-Net residual-block shape
+    kc.check_groupnorm(be, B=2, C=192, HW=100 * 68, G=8, act=1)    # the final norm of the U-Net

@@ -142,3 +142,28 @@ def test_layer_options_and_errors():
         npb.SpectralConv2d(4, 4, (2, 2)).to(DEV)(torch.randn(1, 4, 8, 8, device=DEV, dtype=torch.float64))
     with pytest.raises(NotImplementedError):
         npb.FNO_Layer(hidden_dim=4, num_spatial_dims=1, modes=4)
+
+
+def test_fused_groupnorm_gelu_vs_torch():
+    """Plain PyTorch fp32 reference of the same op: F.gelu(F.group_norm(x)) forward and backward."""
+    from neural_pde_surrogates_b200 import ops
+    torch.manual_seed(0)
+    for (B, C, H, W, G) in [(4, 193, 47, 31, 1), (2, 192, 100, 68, 8)]:
+        norm = torch.nn.GroupNorm(G, C).to(DEV)
+        with torch.no_grad():
+            norm.weight.uniform_(0.5, 1.5)
+            norm.bias.uniform_(-0.3, 0.3)
+        x = (torch.randn(B, C, H, W, device=DEV) * 2 + 0.5).requires_grad_()
+        g = torch.randn(B, C, H, W, device=DEV)
+        act = torch.nn.GELU()
+        y = ops.group_norm_act(x, norm, act)
+        y.backward(g)
+        got = (y.detach().clone(), x.grad.clone(), norm.weight.grad.clone(), norm.bias.grad.clone())
+        x.grad = None; norm.weight.grad = None; norm.bias.grad = None
+        xr = x.detach().double().requires_grad_()
+        nd = torch.nn.GroupNorm(G, C).to(DEV).double()
+        nd.load_state_dict({k: v.double() for k, v in norm.state_dict().items()})
+        yr = torch.nn.functional.gelu(nd(xr))
+        yr.backward(g.double())
+        for a, b in zip(got, (yr, xr.grad, nd.weight.grad, nd.bias.grad)):
+            assert rel_l2(a, b) < 1e-5

@@ -69,6 +69,7 @@ def main():
         pre = torch.empty(B, Cout, H, W, device=dev)
         ws = torch.empty(lib.pdes_block_fwd_workspace_floats(B, Cin, Cout, H, W, m1, m2), device=dev)
         wsb = torch.empty(lib.pdes_block_bwd_workspace_floats(B, C0, C1, Cout, H, W, m1, m2), device=dev)
+        pack = torch.empty(lib.pdes_gemm_tc_pack_floats(Cin, Cout), device=dev)
         gpre = torch.empty_like(g)
         dh = torch.empty_like(h)
         gw1, gw2 = torch.empty_like(w1), torch.empty_like(w2)
@@ -87,6 +88,10 @@ def main():
             "K3b_inv_w_gemm": (lambda: ck(lib.pdes_inv_w_gemm(p(Z), p(wct), Cout, p(h), C0, p(vb), C1, p(bias), p(res),
                                                              p(tab), 0, p(outp), None, B, Cout, H, W, m1, m2, 1, st)),
                                4 * B * Cin * HW + 8 * B * Cout * HW + 4 * B * H * 2 * m2 * Cout),
+            "K3b_tcgen05_3xtf32": (lambda: (ck(lib.pdes_gemm_tc_pack(p(wct), Cout, Cin, Cout, p(pack), st)),
+                                            ck(lib.pdes_inv_w_gemm_tc(p(Z), p(pack), p(h), C0, p(vb), C1, p(bias), p(res), p(tab), 0,
+                                                                      p(outp), None, B, Cout, H, W, m1, m2, 1, st))),
+                                   4 * B * Cin * HW + 8 * B * Cout * HW + 4 * B * H * 2 * m2 * Cout),
             "block_forward": (lambda: ck(lib.pdes_block_forward(p(h), C0, p(vb), C1, p(w1), p(w2), p(wct), p(bias), p(res),
                                                                 p(tab), p(X), p(ws), p(outp), None, B, Cout, H, W, m1, m2, 1, st)),
                               4 * B * Cin * HW + 16 * Cin * Cout * MM + 8 * B * Cout * HW + 4 * Cout * Cin + 4 * Cout),
