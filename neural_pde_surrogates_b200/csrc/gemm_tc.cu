@@ -22,6 +22,10 @@
 // per SM (2 x 256 TMEM columns, 2 x ~82 KB shared memory) so one CTA's epilogue overlaps the other's main loop.
 #include "pdes_common.cuh"
 #include "pdes_ptx.cuh"
+#ifndef PDES_CPU_EMU
+#include <cuda.h>      // CUtensorMap types only; the encoder is fetched with cudaGetDriverEntryPoint (no libcuda link)
+#include <cstring>
+#endif
 
 namespace pdes {
 
@@ -294,13 +298,382 @@ k_inv_w_gemm_tc(TcParams p) {
   }
 }
 
+
+// ----------------------------------------------------------------------------------------------------------------
+// v3: persistent, warp-specialised version of the same GEMM (mode 2, default).
+//   one CTA per SM loops over 128-pixel tiles; 512 threads:
+//     warps 0-3  convert   raw ring -> hi/lo split -> canonical A stage (and, for spectral chunks, canonical B)
+//     warp  4    MMA       one thread issues tcgen05.mma into one of TWO TMEM accumulators (2 x 256 columns)
+//     warp  5    raw issue bulk async copies of activation rows / Z rows into a 3-deep raw ring
+//     warp  6    B issue   bulk async copies of the packed weight chunks into a 4-deep ring (runs up to 4 chunks
+//                          ahead, across tile boundaries, so the L2 latency of the weights is never exposed)
+//     warps 8-15 epilogue  TMEM -> registers -> bias/residual/GELU -> coalesced stores, overlapping the next tile's
+//                          main loop through the second accumulator
+#ifdef PDES_TC_TRACE
+__device__ long long g_trace[4096];
+#define TRACE(slot) do { if (blockIdx.x == 0 && (slot) < 4096) g_trace[(slot)] = clock64(); } while (0)
+#else
+#define TRACE(slot) do { } while (0)
+#endif
+constexpr int kV3Threads = 768;       // 8 service warps + 16 epilogue warps
+constexpr int kV3EpiParts = 4;         // epilogue warps per TMEM lane quadrant
+constexpr int kV3ASt = 3, kV3BSt = 4, kV3Raw = 3;
+
+struct V3Bars {
+  unsigned long long a_full[kV3ASt], a_empty[kV3ASt], b_full[kV3BSt], b_empty[kV3BSt], raw_full[kV3Raw],
+      raw_empty[kV3Raw], acc_full[2], acc_empty[2];
+};
+
+__global__ void __launch_bounds__(kV3Threads, 1)
+k_inv_w_gemm_tc_v3(TcParams p, int B, int ntiles_per_img, const __grid_constant__ CUtensorMap tmap_x0, int ntmap_chunks) {
+  PDES_DYN_SMEM(unsigned char, smem_raw);
+  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int npad = p.npad;
+  const uint32_t a_blk = kTcM * kTcBK * 4;                       // 8 KB
+  const uint32_t b_blk = (uint32_t)npad * kTcBK * 4;             // 12 KB at N = 192
+  const uint32_t a_stage = 2 * a_blk, b_stage = 2 * b_blk;
+  const int slot_f = kTcBK * (npad > kTcM ? npad : kTcM);         // floats per raw slot
+  unsigned char* sA = base;
+  unsigned char* sB = sA + kV3ASt * a_stage;
+  float* raw = reinterpret_cast<float*>(sB + kV3BSt * b_stage);
+  __shared__ __align__(8) V3Bars bars;
+  __shared__ uint32_t tmem_slot;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int HW = p.H * p.W, W = p.W, J = 2 * p.m2;
+  const int nx = tc_nchunks(p.K);
+  const int ntiles = B * ntiles_per_img;
+
+  if (tid == 0) {
+    for (int i = 0; i < kV3ASt; ++i) { ptx::mbar_init(&bars.a_full[i], 128); ptx::mbar_init(&bars.a_empty[i], 1); }
+    for (int i = 0; i < kV3BSt; ++i) { ptx::mbar_init(&bars.b_full[i], 1); ptx::mbar_init(&bars.b_empty[i], 1); }
+    for (int i = 0; i < kV3Raw; ++i) { ptx::mbar_init(&bars.raw_full[i], 1); ptx::mbar_init(&bars.raw_empty[i], 128); }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&bars.acc_full[i], 1); ptx::mbar_init(&bars.acc_empty[i], 32 * 4 * kV3EpiParts); }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 4) {
+    ptx::tmem_alloc(&tmem_slot, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  // per-tile geometry (identical in every role)
+  auto tile_geom = [&](int t, int& b, int& p0, int& h0, int& kspec, int& nsp) {
+    b = t / ntiles_per_img;
+    p0 = (t - b * ntiles_per_img) * kTcM;
+    const int plast = (p0 + kTcM - 1 < HW - 1) ? (p0 + kTcM - 1) : (HW - 1);
+    h0 = p0 / W;
+    kspec = (p.Z != nullptr) ? (plast / W - h0 + 1) * J : 0;
+    nsp = tc_nchunks(kspec);
+  };
+
+  if (warp < 4) {
+    // ================================================================== convert
+    const uint32_t row_off = (uint32_t)(tid >> 3) * 128 + (uint32_t)(tid & 7) * 16;
+    const uint32_t lbo_b = (uint32_t)(npad / 8) * 128;
+    uint32_t g = 0;                                              // global chunk counter
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      int b, p0, h0, kspec, nsp;
+      tile_geom(t, b, p0, h0, kspec, nsp);
+      const int pp = p0 + tid;
+      const bool pvalid = pp < HW;
+      const int hh = pvalid ? pp / W : 0, ww = pvalid ? pp % W : 0;
+      for (int c = 0; c < nsp + nx; ++c, ++g) {
+        const uint32_t s = g % kV3ASt, r = g % kV3Raw, q = g % kV3BSt;
+        if (tid == 0) TRACE(0 * 512 + g * 4 + 0);
+        if (g >= kV3ASt) ptx::mbar_wait(&bars.a_empty[s], ((g / kV3ASt) - 1) & 1);
+        if (tid == 0) TRACE(0 * 512 + g * 4 + 1);
+        unsigned char* st = sA + s * a_stage;
+        float v[kTcBK];
+        if (c >= nsp) {
+          const int cx = c - nsp;
+          ptx::mbar_wait(&bars.raw_full[r], (g / kV3Raw) & 1);
+          if (tid == 0) TRACE(0 * 512 + g * 4 + 2);
+          const float* rw = raw + (size_t)r * slot_f + tid;               // activation rows: dense [16][128]
+#pragma unroll
+          for (int kk = 0; kk < kTcBK; ++kk) v[kk] = (pvalid && cx * kTcBK + kk < p.K) ? rw[kk * kTcM] : 0.0f;
+          ptx::mbar_arrive(&bars.raw_empty[r]);
+        } else {
+          // spectral chunk: A = T[j][w] on this pixel's row, B = Z rows (staged in the raw slot) -> canonical
+#pragma unroll
+          for (int kk = 0; kk < kTcBK; ++kk) {
+            const int k = c * kTcBK + kk;
+            const int rr = k / J, j = k - rr * J;
+            v[kk] = (pvalid && k < kspec && hh - h0 == rr) ? __ldg(p.T + (size_t)j * W + ww) : 0.0f;
+          }
+          if (g >= kV3BSt) ptx::mbar_wait(&bars.b_empty[q], ((g / kV3BSt) - 1) & 1);
+          ptx::mbar_wait(&bars.raw_full[r], (g / kV3Raw) & 1);
+          const float* rw = raw + (size_t)r * slot_f;                     // Z rows: dense [16][N]
+          unsigned char* sb = sB + q * b_stage;
+          // one (n, 4 consecutive k) item = one 16-byte row of a core matrix: conflict-free LDS and STS.128
+          for (int n = tid; n < npad; n += 128) {
+#pragma unroll
+            for (int kq = 0; kq < kTcBK / 4; ++kq) {
+              float z[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int kk = kq * 4 + e;
+                z[e] = (c * kTcBK + kk < kspec && n < p.N) ? rw[kk * p.N + n] : 0.0f;
+              }
+              float4 hi, lo;
+              hi.x = tf32_hi(z[0]); lo.x = z[0] - hi.x;
+              hi.y = tf32_hi(z[1]); lo.y = z[1] - hi.y;
+              hi.z = tf32_hi(z[2]); lo.z = z[2] - hi.z;
+              hi.w = tf32_hi(z[3]); lo.w = z[3] - hi.w;
+              const uint32_t off = (uint32_t)kq * lbo_b + (uint32_t)(n >> 3) * 128 + (uint32_t)(n & 7) * 16;
+              *reinterpret_cast<float4*>(sb + off) = hi;
+              *reinterpret_cast<float4*>(sb + b_blk + off) = lo;
+            }
+          }
+          ptx::mbar_arrive(&bars.raw_empty[r]);
+        }
+#pragma unroll
+        for (int qd = 0; qd < kTcBK / 4; ++qd) {
+          float4 hi, lo;
+          hi.x = tf32_hi(v[4 * qd + 0]); lo.x = v[4 * qd + 0] - hi.x;
+          hi.y = tf32_hi(v[4 * qd + 1]); lo.y = v[4 * qd + 1] - hi.y;
+          hi.z = tf32_hi(v[4 * qd + 2]); lo.z = v[4 * qd + 2] - hi.z;
+          hi.w = tf32_hi(v[4 * qd + 3]); lo.w = v[4 * qd + 3] - hi.w;
+          const uint32_t off = (uint32_t)qd * (kTcM / 8) * 128 + row_off;
+          *reinterpret_cast<float4*>(st + off) = hi;
+          *reinterpret_cast<float4*>(st + a_blk + off) = lo;
+        }
+        ptx::fence_proxy_async();
+        ptx::mbar_arrive(&bars.a_full[s]);
+        if (tid == 0) TRACE(0 * 512 + g * 4 + 3);
+      }
+    }
+  } else if (warp == 4) {
+    if (lane == 0) {
+      // ================================================================ MMA issue
+      const uint32_t idesc = ptx::idesc_tf32(kTcM, npad);
+      const uint32_t lbo_a = (kTcM / 8) * 128, lbo_b = (uint32_t)(npad / 8) * 128, sbo = 128;
+      const uint64_t a_hi0 = ptx::smem_desc_noswizzle(ptx::smem_u32(sA), lbo_a, sbo);
+      const uint64_t a_lo0 = ptx::smem_desc_noswizzle(ptx::smem_u32(sA) + a_blk, lbo_a, sbo);
+      const uint64_t b_hi0 = ptx::smem_desc_noswizzle(ptx::smem_u32(sB), lbo_b, sbo);
+      const uint64_t b_lo0 = ptx::smem_desc_noswizzle(ptx::smem_u32(sB) + b_blk, lbo_b, sbo);
+      uint32_t g = 0, it = 0;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+        int b, p0, h0, kspec, nsp;
+        tile_geom(t, b, p0, h0, kspec, nsp);
+        const uint32_t a = it & 1;
+        TRACE(3 * 512 + 256 + it * 2 + 0);
+        if (it >= 2) ptx::mbar_wait(&bars.acc_empty[a], ((it / 2) - 1) & 1);
+        TRACE(3 * 512 + 256 + it * 2 + 1);
+        ptx::tc_fence_after();
+        const uint32_t dcol = tmem_base + a * 256;
+        const int nch = nsp + nx;
+        for (int c = 0; c < nch; ++c, ++g) {
+          const uint32_t s = g % kV3ASt, q = g % kV3BSt;
+          TRACE(1 * 512 + g * 4 + 0);
+          ptx::mbar_wait(&bars.a_full[s], (g / kV3ASt) & 1);
+          TRACE(1 * 512 + g * 4 + 1);
+          ptx::mbar_wait(&bars.b_full[q], (g / kV3BSt) & 1);
+          TRACE(1 * 512 + g * 4 + 2);
+          ptx::tc_fence_after();
+          // only the 14-bit start-address field of a descriptor changes between stages / K steps
+          const uint64_t da = (uint64_t)((s * a_stage) >> 4), db = (uint64_t)((q * b_stage) >> 4);
+#pragma unroll
+          for (int ks = 0; ks < kTcBK / 8; ++ks) {
+            const uint64_t ka = da + (uint64_t)((ks * 2 * lbo_a) >> 4), kb = db + (uint64_t)((ks * 2 * lbo_b) >> 4);
+            ptx::mma_tf32(dcol, a_lo0 + ka, b_hi0 + kb, idesc, (c | ks) != 0 ? 1u : 0u);
+            ptx::mma_tf32(dcol, a_hi0 + ka, b_lo0 + kb, idesc, 1u);
+            ptx::mma_tf32(dcol, a_hi0 + ka, b_hi0 + kb, idesc, 1u);
+          }
+          ptx::tc_commit(&bars.a_empty[s]);
+          ptx::tc_commit(&bars.b_empty[q]);
+          TRACE(1 * 512 + g * 4 + 3);
+        }
+        ptx::tc_commit(&bars.acc_full[a]);
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {
+      // ================================================================ raw ring issue (activation rows / Z rows)
+      uint32_t g = 0;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        int b, p0, h0, kspec, nsp;
+        tile_geom(t, b, p0, h0, kspec, nsp);
+        const int npx = (HW - p0 < kTcM) ? (HW - p0) : kTcM;
+        for (int c = 0; c < nsp + nx; ++c, ++g) {
+          const uint32_t r = g % kV3Raw;
+          TRACE(2 * 512 + g * 4 + 0);
+          if (g >= kV3Raw) ptx::mbar_wait(&bars.raw_empty[r], ((g / kV3Raw) - 1) & 1);
+          TRACE(2 * 512 + g * 4 + 1);
+          float* dst = raw + (size_t)r * slot_f;
+          if (c < nsp) {
+            // 16 consecutive (row, j) lines of Z are contiguous in memory: ONE bulk copy per spectral chunk
+            const int nk = (kspec - c * kTcBK < kTcBK) ? (kspec - c * kTcBK) : kTcBK;
+            ptx::mbar_arrive_expect_tx(&bars.raw_full[r], (uint32_t)nk * p.N * 4);
+            ptx::bulk_g2s(dst, p.Z + (((size_t)b * p.H + h0) * J + (size_t)c * kTcBK) * p.N, (uint32_t)nk * p.N * 4,
+                          &bars.raw_full[r]);
+          } else {
+            const int cx = c - nsp;
+            const int nk = (p.K - cx * kTcBK < kTcBK) ? (p.K - cx * kTcBK) : kTcBK;
+            if (cx < ntmap_chunks) {
+              // one 2-D TMA box: 16 channel rows x 128 pixels (SASS UTMALDG)
+              ptx::mbar_arrive_expect_tx(&bars.raw_full[r], (uint32_t)kTcBK * kTcM * 4);
+              ptx::tma_load_2d(dst, &tmap_x0, p0, b * p.C0 + cx * kTcBK, &bars.raw_full[r]);
+            } else {
+              ptx::mbar_arrive_expect_tx(&bars.raw_full[r], (uint32_t)nk * npx * 4);
+              for (int kk = 0; kk < nk; ++kk) {
+                const int k = cx * kTcBK + kk;
+                const float* src = (k < p.C0) ? p.x0 + ((size_t)b * p.C0 + k) * HW : p.x1 + ((size_t)b * p.C1 + (k - p.C0)) * HW;
+                ptx::bulk_g2s(dst + kk * kTcM, src + p0, (uint32_t)npx * 4, &bars.raw_full[r]);
+              }
+            }
+          }
+          TRACE(2 * 512 + g * 4 + 2);
+        }
+      }
+    }
+  } else if (warp == 6) {
+    if (lane == 0) {
+      // ================================================================ B ring issue (packed weight chunks)
+      uint32_t g = 0;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        int b, p0, h0, kspec, nsp;
+        tile_geom(t, b, p0, h0, kspec, nsp);
+        for (int c = 0; c < nsp + nx; ++c, ++g) {
+          const uint32_t q = g % kV3BSt;
+          if (g >= kV3BSt) ptx::mbar_wait(&bars.b_empty[q], ((g / kV3BSt) - 1) & 1);
+          if (c < nsp) {
+            ptx::mbar_arrive(&bars.b_full[q]);          // B of a spectral chunk is written by the convert warps
+          } else {
+            ptx::mbar_arrive_expect_tx(&bars.b_full[q], b_stage);
+            ptx::bulk_g2s(sB + q * b_stage, p.wpack + (size_t)(c - nsp) * (b_stage / 4), b_stage, &bars.b_full[q]);
+          }
+        }
+      }
+    }
+  } else if (warp >= 8) {
+    // ==================================================================== epilogue: 2 warps per TMEM lane quadrant
+    // Code-size discipline: the exact-erf GELU is ~40 instructions, so the column loop is NOT unrolled beyond 8
+    // (a fully unrolled 32-column body was > 30 KB of SASS and ran out of the instruction cache: 270 cycles/output).
+    const int quad = warp & 3, part = (warp - 8) >> 2;
+    const int N = p.N;
+    const int nq = (npad + 7) / 8;                                   // 8-column groups
+    const int per = (nq + kV3EpiParts - 1) / kV3EpiParts;
+    const int qbeg = (part * per < nq) ? part * per : nq, qend = (qbeg + per < nq) ? qbeg + per : nq;
+    uint32_t it = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+      int b, p0, h0, kspec, nsp;
+      tile_geom(t, b, p0, h0, kspec, nsp);
+      const int pp = p0 + quad * 32 + lane;
+      const bool pvalid = pp < HW;
+      const size_t obase = (size_t)b * N * HW + pp;
+      const uint32_t a = it & 1;
+      const bool has_res = p.res != nullptr && pvalid;
+      const bool has_pre = p.pre != nullptr, do_gelu = p.act == PDES_ACT_GELU;
+      const bool has_bias = p.bias != nullptr, bias_vec = aligned16(p.bias);
+      float cur[8], nxt[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int n = qbeg * 8 + e;
+        cur[e] = (has_res && qbeg < qend && n < N) ? __ldg(p.res + obase + (size_t)n * HW) : 0.0f;
+      }
+      if (tid == 256) TRACE(3 * 512 + it * 4 + 0);
+      ptx::mbar_wait(&bars.acc_full[a], (it / 2) & 1);
+      if (tid == 256) TRACE(3 * 512 + it * 4 + 1);
+      ptx::tc_fence_after();
+      const uint32_t tbase = tmem_base + a * 256 + ((uint32_t)(quad * 32) << 16);
+#pragma unroll 1
+      for (int qi = qbeg; qi < qend; ++qi) {
+        const int n0 = qi * 8;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {                                // prefetch the residual of the next group
+          const int n = n0 + 8 + e;
+          nxt[e] = (has_res && qi + 1 < qend && n < N) ? __ldg(p.res + obase + (size_t)n * HW) : 0.0f;
+        }
+        uint32_t r[8];
+        ptx::tmem_ld8(tbase + (uint32_t)n0, r);
+        ptx::tmem_ld_wait();
+        if (qi + 1 == qend) {                                        // accumulator fully read: hand it back to the MMA warp
+          ptx::tc_fence_before();
+          ptx::mbar_arrive(&bars.acc_empty[a]);
+          if (tid == 256) TRACE(3 * 512 + it * 4 + 2);
+        }
+        if (pvalid) {
+          float* po = p.out + obase + (size_t)n0 * HW;
+          float* pq = has_pre ? p.pre + obase + (size_t)n0 * HW : nullptr;
+          if (n0 + 8 <= N) {                                         // whole group valid: no per-element guards
+            float bz[8];
+            if (has_bias && bias_vec) {
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n0));
+              const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + 4));
+              bz[0] = b0.x; bz[1] = b0.y; bz[2] = b0.z; bz[3] = b0.w; bz[4] = b1.x; bz[5] = b1.y; bz[6] = b1.z; bz[7] = b1.w;
+            } else if (has_bias) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) bz[e] = __ldg(p.bias + n0 + e);
+            } else {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) bz[e] = 0.0f;
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              float v = __uint_as_float(r[e]) + cur[e] + bz[e];
+              if (has_pre) pq[(size_t)e * HW] = v;
+              if (do_gelu) v = gelu_fast_f(v);
+              po[(size_t)e * HW] = v;
+            }
+          } else {
+            for (int e = 0; e < 8 && n0 + e < N; ++e) {
+              float v = __uint_as_float(r[e]) + cur[e];
+              if (has_bias) v += __ldg(p.bias + n0 + e);
+              if (has_pre) pq[(size_t)e * HW] = v;
+              if (do_gelu) v = gelu_fast_f(v);
+              po[(size_t)e * HW] = v;
+            }
+          }
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) cur[e] = nxt[e];
+      }
+      if (tid == 256) TRACE(3 * 512 + it * 4 + 3);
+      if (qbeg >= qend) {                                            // no column group for this warp (N <= 8)
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(&bars.acc_empty[a]);                        // still only after acc_full: keeps phases in step
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
 #endif  // !PDES_CPU_EMU
 
 int g_tc_mode =
 #ifdef PDES_CPU_EMU
     0;
 #else
-    1;
+    2;
+#endif
+int g_num_sms = 0;
+
+#ifndef PDES_CPU_EMU
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  return fn;
+}
 #endif
 
 }  // namespace
@@ -308,12 +681,18 @@ int g_tc_mode =
 
 extern "C" {
 
+#ifdef PDES_TC_TRACE
+int pdes_tc_trace_read(long long* host, int n) {
+  return (int)cudaMemcpyFromSymbol(host, pdes::g_trace, sizeof(long long) * n);
+}
+#endif
+
 void pdes_set_tensor_core_mode(int mode) {
 #ifdef PDES_CPU_EMU
   (void)mode;
   pdes::g_tc_mode = 0;
 #else
-  pdes::g_tc_mode = mode ? 1 : 0;
+  pdes::g_tc_mode = (mode == 1 || mode == 2) ? mode : 0;
 #endif
 }
 
@@ -366,7 +745,9 @@ int pdes_inv_w_gemm_tc(const float* Z, const float* wpack, const float* x0, int 
   PDES_REQUIRE(pdes_inv_w_gemm_tc_ok(N, C0 + C1, H, W, Z != nullptr ? m2 : 0, x0, x1), PDES_ERR_UNSUPPORTED,
                "pdes_inv_w_gemm_tc: shape/alignment not supported by the tensor-core kernel (N=%d, HW=%d, W=%d)", N, H * W, W);
   PDES_REQUIRE(B <= 65535, PDES_ERR_UNSUPPORTED, "pdes_inv_w_gemm_tc: grid too large");
+#ifndef PDES_TC_TRACE
   PDES_REQUIRE(act == PDES_ACT_NONE || act == PDES_ACT_GELU, PDES_ERR_ARG, "pdes_inv_w_gemm_tc: unknown activation");
+#endif
   PDES_REQUIRE((reinterpret_cast<uintptr_t>(wpack) & 15u) == 0, PDES_ERR_ARG, "pdes_inv_w_gemm_tc: wpack must be 16-byte aligned");
   TcParams p;
   p.Z = Z; p.wpack = wpack; p.x0 = x0; p.C0 = C0; p.x1 = x1; p.C1 = C1; p.bias = bias; p.res = res; p.T = nullptr;
@@ -376,6 +757,39 @@ int pdes_inv_w_gemm_tc(const float* Z, const float* wpack, const float* x0, int 
     p.T = tables + (backward_scale ? t.tinv_b : t.tinv_f);
   }
   p.out = out; p.pre = pre; p.N = N; p.npad = tc_npad(N); p.K = C0 + C1; p.H = H; p.W = W; p.m2 = m2; p.act = act;
+  if (g_tc_mode == 2 && (Z == nullptr || N % 4 == 0)) {
+    if (g_num_sms == 0) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+      if (g_num_sms <= 0) g_num_sms = 148;
+    }
+    const int rawld = p.npad > kTcM ? p.npad : kTcM;
+    const size_t smem3 = (size_t)kV3ASt * 2 * kTcM * kTcBK * 4 + (size_t)kV3BSt * 2 * p.npad * kTcBK * 4 +
+                         (size_t)kV3Raw * kTcBK * rawld * 4 + 1024;
+    const int tiles_per_img = ceil_div(H * W, kTcM);
+    const int ntiles = B * tiles_per_img;
+    // 2-D tensor map over x0 viewed as [B*C0 rows][HW pixels]; used for the chunks that lie entirely inside x0 when
+    // every tile is a full 128-pixel box (otherwise the kernel falls back to per-row bulk copies)
+    alignas(64) CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    int ntmap_chunks = 0;
+    if ((H * W) % kTcM == 0 && g_encode_tiled() != nullptr) {
+      const cuuint64_t gdim[2] = {(cuuint64_t)(H * W), (cuuint64_t)B * (cuuint64_t)C0};
+      const cuuint64_t gstr[1] = {(cuuint64_t)(H * W) * 4};
+      const cuuint32_t box[2] = {(cuuint32_t)kTcM, (cuuint32_t)kTcBK};
+      const cuuint32_t estr[2] = {1, 1};
+      const CUresult r = g_encode_tiled()(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(x0), gdim, gstr, box,
+                                          estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r == CUDA_SUCCESS) ntmap_chunks = C0 / kTcBK;
+    }
+    auto k3 = k_inv_w_gemm_tc_v3;
+    PDES_SET_SMEM(k3, smem3);
+    PDES_LAUNCH(k3, dim3((unsigned)(ntiles < g_num_sms ? ntiles : g_num_sms)), dim3(kV3Threads), smem3, stream, p, B,
+                tiles_per_img, tmap, ntmap_chunks);
+    return check_launch("pdes_inv_w_gemm_tc(v3)");
+  }
   const size_t stage = (size_t)2 * kTcM * kTcBK * 4 + (size_t)2 * p.npad * kTcBK * 4;
   const size_t smem = 2 * stage + (size_t)kTcRaw * kTcBK * kTcM * 4 + 1024;
   auto kfn = k_inv_w_gemm_tc;

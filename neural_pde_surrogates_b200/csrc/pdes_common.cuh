@@ -69,6 +69,26 @@ __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; 
 
 // exact GELU and its derivative (nn.GELU() default, approximate='none')
 __device__ __forceinline__ float gelu_f(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f)); }
+// GELU with erf from Abramowitz-Stegun 7.1.26 (|erf error| <= 6e-7 in fp32 => GELU rel. L2 error ~1e-7, two orders
+// below the 1e-5 parity budget) in ~16 instructions instead of ~34: used where the epilogue is issue-bound.
+__device__ __forceinline__ float gelu_fast_f(float v) {
+  const float x = v * 0.70710678118654752440f;
+  const float ax = fabsf(x);
+#ifdef PDES_CPU_EMU
+  const float t = 1.0f / fmaf(0.3275911f, ax, 1.0f);
+  const float ex = expf(-ax * ax);
+#else
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
+  const float ex = __expf(-ax * ax);
+#endif
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  poly *= t;
+  const float e = 1.0f - poly * ex;
+  return 0.5f * v * (1.0f + copysignf(e, x));
+}
 __device__ __forceinline__ float gelu_grad_f(float v) {
   const float cdf = 0.5f * (1.0f + erff(v * 0.70710678118654752440f));
   const float pdf = 0.39894228040143267794f * expf(-0.5f * v * v);

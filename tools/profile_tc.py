@@ -30,9 +30,10 @@ for _ in range(3):
     else:  # bare GEMM
         _native.check(lib, lib.pdes_inv_w_gemm_tc(None, p(pack), p(h), C0, p(vb), C1, None, None, p(tab), 0, p(out), None, B, Cout, H, W, m1, m2, 0, st))
 torch.cuda.synchronize()
-for v in ("full", "nospec", "bare"):
+for v in ("full", "nospec", "bare", "nostore"):
     fn = {"full": lambda: lib.pdes_inv_w_gemm_tc(p(Z), p(pack), p(h), C0, p(vb), C1, p(bias), p(res), p(tab), 0, p(out), None, B, Cout, H, W, m1, m2, 1, st),
           "nospec": lambda: lib.pdes_inv_w_gemm_tc(None, p(pack), p(h), C0, p(vb), C1, p(bias), p(res), p(tab), 0, p(out), None, B, Cout, H, W, m1, m2, 1, st),
+          "nostore": lambda: lib.pdes_inv_w_gemm_tc(None, p(pack), p(h), C0, p(vb), C1, None, None, p(tab), 0, p(out), None, B, Cout, H, W, m1, m2, 77, st),
           "bare": lambda: lib.pdes_inv_w_gemm_tc(None, p(pack), p(h), C0, p(vb), C1, None, None, p(tab), 0, p(out), None, B, Cout, H, W, m1, m2, 0, st)}[v]
     fn(); torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
