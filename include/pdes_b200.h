@@ -90,8 +90,10 @@ int pdes_inv_w_gemm(const float* Z, const float* At, int lda, const float* x0, i
 /* ---- K3b on the tensor cores (tcgen05 + TMEM, 3xTF32 split => fp32-faithful, rel. error ~2^-21 per product) -----
  * Same contract as pdes_inv_w_gemm but the 1x1-conv weights come pre-packed by pdes_gemm_tc_pack (hi/lo TF32 split
  * in the UMMA canonical K-major layout, one contiguous block per 16-channel chunk so it can be fetched with a bulk
- * async copy).  Requires N <= 256 output channels.  `pdes_set_tensor_core_mode(1)` (default on sm_100a) makes the
- * fused chains below use this kernel; mode 0 keeps every multiply on fp32 FFMA. */
+ * async copy).  Requires N <= 256 output channels.  pdes_set_tensor_core_mode: 0 = every multiply on fp32 FFMA;
+ * 1 = tcgen05 3xTF32, one tile per CTA (first version, kept for comparison); 2 = tcgen05 3xTF32, persistent
+ * warp-specialised kernel (default on sm_100a); 3 = the same kernel with a single TF32 pass (hi*hi only): NOT
+ * fp32-faithful (rel. error ~5e-4), offered as the separately reported reduced-precision mode. */
 void pdes_set_tensor_core_mode(int mode);
 int pdes_get_tensor_core_mode(void);
 int pdes_gemm_tc_supported(int N, int K);

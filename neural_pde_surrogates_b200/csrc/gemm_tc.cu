@@ -74,6 +74,7 @@ struct TcParams {
   float* out;
   float* pre;
   int N, npad, K, H, W, m2, act;
+  int single_pass;      // 1 = plain TF32 (hi*hi only): the separately reported reduced-precision mode
 };
 
 constexpr int kTcRaw = 3;          // depth of the raw activation ring fed by bulk async copies
@@ -479,9 +480,13 @@ k_inv_w_gemm_tc_v3(TcParams p, int B, int ntiles_per_img, const __grid_constant_
 #pragma unroll
           for (int ks = 0; ks < kTcBK / 8; ++ks) {
             const uint64_t ka = da + (uint64_t)((ks * 2 * lbo_a) >> 4), kb = db + (uint64_t)((ks * 2 * lbo_b) >> 4);
-            ptx::mma_tf32(dcol, a_lo0 + ka, b_hi0 + kb, idesc, (c | ks) != 0 ? 1u : 0u);
-            ptx::mma_tf32(dcol, a_hi0 + ka, b_lo0 + kb, idesc, 1u);
-            ptx::mma_tf32(dcol, a_hi0 + ka, b_hi0 + kb, idesc, 1u);
+            if (p.single_pass) {
+              ptx::mma_tf32(dcol, a_hi0 + ka, b_hi0 + kb, idesc, (c | ks) != 0 ? 1u : 0u);
+            } else {
+              ptx::mma_tf32(dcol, a_lo0 + ka, b_hi0 + kb, idesc, (c | ks) != 0 ? 1u : 0u);
+              ptx::mma_tf32(dcol, a_hi0 + ka, b_lo0 + kb, idesc, 1u);
+              ptx::mma_tf32(dcol, a_hi0 + ka, b_hi0 + kb, idesc, 1u);
+            }
           }
           ptx::tc_commit(&bars.a_empty[s]);
           ptx::tc_commit(&bars.b_empty[q]);
@@ -692,7 +697,7 @@ void pdes_set_tensor_core_mode(int mode) {
   (void)mode;
   pdes::g_tc_mode = 0;
 #else
-  pdes::g_tc_mode = (mode == 1 || mode == 2) ? mode : 0;
+  pdes::g_tc_mode = (mode >= 1 && mode <= 3) ? mode : 0;
 #endif
 }
 
@@ -757,7 +762,8 @@ int pdes_inv_w_gemm_tc(const float* Z, const float* wpack, const float* x0, int 
     p.T = tables + (backward_scale ? t.tinv_b : t.tinv_f);
   }
   p.out = out; p.pre = pre; p.N = N; p.npad = tc_npad(N); p.K = C0 + C1; p.H = H; p.W = W; p.m2 = m2; p.act = act;
-  if (g_tc_mode == 2 && (Z == nullptr || N % 4 == 0)) {
+  p.single_pass = (g_tc_mode == 3) ? 1 : 0;
+  if (g_tc_mode >= 2 && (Z == nullptr || N % 4 == 0)) {
     if (g_num_sms == 0) {
       int dev = 0;
       cudaGetDevice(&dev);

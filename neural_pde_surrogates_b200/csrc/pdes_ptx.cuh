@@ -43,6 +43,14 @@ __device__ __forceinline__ void mbar_wait(void* bar, uint32_t parity) {
   }
 }
 
+// per-thread 8-byte async copy global -> shared (SASS LDGSTS): deep prefetch without holding registers
+__device__ __forceinline__ void cp_async8(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // 1-D bulk async copy global -> shared, completion counted in bytes on an mbarrier (src/dst/size 16-byte aligned)
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, void* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(

@@ -34,17 +34,36 @@ k_inv_h(const float2* __restrict__ P, int nsplit, int B, int C, int H, int m1, i
   const int c0 = blockIdx.x * kIhOT, b = blockIdx.y;
 
   for (int i = tid; i < H; i += kIhThreads) twh[i] = make_float2(__ldg(twh_g + 2 * i), __ldg(twh_g + 2 * i + 1));
-  for (int idx = tid; idx < kIhOT * M2; idx += kIhThreads) {
-    const int oo = idx / M2, m = idx - oo * M2;
-    float2 v = make_float2(0.f, 0.f);
-    if (c0 + oo < C) {
-      const float2* src = P + ((size_t)b * C + c0 + oo) * M2 + m;
-      for (int s = 0; s < nsplit; ++s) {
-        const float2 pv = __ldg(src + (size_t)s * B * C * M2);
-        v.x += pv.x; v.y += pv.y;
+  // sum the K2 split partials: 8 elements per thread per batch, all loads of one split issued back to back
+  {
+    constexpr int UN = 8;
+    const size_t sstride = (size_t)B * C * M2;
+    for (int base0 = tid; base0 < kIhOT * M2; base0 += kIhThreads * UN) {
+      const float2* src[UN];
+      int dst[UN];
+      float2 a[UN];
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        const int idx = base0 + u * kIhThreads;
+        const int oo = idx / M2, m = idx - oo * M2;
+        const bool ok = idx < kIhOT * M2 && c0 + oo < C;
+        src[u] = ok ? P + ((size_t)b * C + c0 + oo) * M2 + m : nullptr;
+        dst[u] = (idx < kIhOT * M2) ? m * kIhLd + oo : -1;
+        a[u] = make_float2(0.f, 0.f);
       }
+      for (int sp = 0; sp < nsplit; ++sp) {
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+          if (src[u] != nullptr) {
+            const float2 pv = __ldg(src[u] + (size_t)sp * sstride);
+            a[u].x += pv.x; a[u].y += pv.y;
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UN; ++u)
+        if (dst[u] >= 0) Os[dst[u]] = a[u];
     }
-    Os[(size_t)m * kIhLd + oo] = v;
   }
   __syncthreads();
 
