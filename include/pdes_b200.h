@@ -104,6 +104,13 @@ int pdes_inv_w_gemm_tc(const float* Z, const float* wpack, const float* x0, int 
                        const float* bias, const float* res, const float* tables, int backward_scale,
                        float* out, float* pre, int B, int N, int H, int W, int m1, int m2, int act, void* stream);
 
+/* 1x1-conv weight / bias gradient on tcgen05 (3xTF32), same contract as pdes_wgrad below; ws needs
+ * pdes_wgrad_tc_workspace_floats() floats.  Returns PDES_ERR_UNSUPPORTED for shapes it does not cover
+ * (M > 256, K + 1 > 256, H*W % 16 != 0, unaligned pointers): the caller then uses pdes_wgrad. */
+size_t pdes_wgrad_tc_workspace_floats(int M, int K);
+int pdes_wgrad_tc(const float* g, const float* x0, int C0, const float* x1, int C1, float* dW, float* dbias,
+                  float* ws, int B, int M, int HW, void* stream);
+
 /* ---- pointwise / small helpers ------------------------------------------------------------------------
  * g_pre = g_out * act'(pre)  (GeluBackward of proc_ufno.py:118) */
 int pdes_act_bwd(const float* g_out, const float* pre, float* g_pre, size_t n, int act, void* stream);

@@ -28,7 +28,9 @@ BwdWs bwd_ws(int B, int Cin, int C0, int Cout, int H, int W, int m1, int m2, boo
   w.PX = w.GO + round4((size_t)B * Cout * M2 * 2);
   w.Zg = w.PX + round4((size_t)w.nsplit * B * C0 * M2 * 2);
   w.WG = w.Zg + round4((size_t)B * H * 2 * m2 * C0);
-  w.PK = w.WG + (has_conv ? round4(pdes_wgrad_workspace_floats(B, Cout, Cin, H * W)) : 0);
+  size_t wg = has_conv ? pdes_wgrad_workspace_floats(B, Cout, Cin, H * W) : 0;
+  if (has_conv && pdes_wgrad_tc_workspace_floats(Cout, Cin) > wg) wg = pdes_wgrad_tc_workspace_floats(Cout, Cin);
+  w.PK = w.WG + round4(wg);
   w.total = w.PK + (has_conv ? round4(pdes_gemm_tc_pack_floats(Cout, C0)) : 0);
   return w;
 }
@@ -110,7 +112,10 @@ int pdes_block_backward(const float* g_out, const float* pre, const float* h, in
     return e;
   }
   if (has_conv && (dwc != nullptr || dbias != nullptr)) {
-    if (int e = pdes_wgrad(gp, h, C0, vb, C1, dwc, dbias, WG, B, Cout, H * W, stream)) return e;
+    int e = PDES_ERR_UNSUPPORTED;
+    if (pdes_get_tensor_core_mode() >= 2) e = pdes_wgrad_tc(gp, h, C0, vb, C1, dwc, dbias, WG, B, Cout, H * W, stream);
+    if (e == PDES_ERR_UNSUPPORTED) e = pdes_wgrad(gp, h, C0, vb, C1, dwc, dbias, WG, B, Cout, H * W, stream);
+    if (e) return e;
   }
   return PDES_OK;
 }

@@ -32,6 +32,7 @@ namespace pdes {
 constexpr int kTcBK = 16;          // channels per pipeline stage
 constexpr int kTcM = 128;          // pixels per CTA tile
 constexpr int kTcMaxN = 256;
+constexpr int kWgtMaxCtas = 160;   // upper bound on the CTAs (= partial sums) of the tensor-core weight-gradient kernel
 
 __host__ __device__ inline int tc_npad(int N) { return (N + 15) & ~15; }
 __host__ __device__ inline int tc_nchunks(int K) { return (K + kTcBK - 1) / kTcBK; }
@@ -652,6 +653,191 @@ k_inv_w_gemm_tc_v3(TcParams p, int B, int ntiles_per_img, const __grid_constant_
   }
 }
 
+
+// ----------------------------------------------------------------------------------------------------------------
+// 1x1-conv weight gradient on tcgen05:  dW[o][i] = sum_{b,p} g[b][o][p] * xin[b][i][p]   (+ ones column = dbias)
+// GEMM: M = output channels (two overlapping 128-row tiles), N = input channels + 1, K = pixels.  Both operands are
+// pixel-contiguous in HBM, i.e. natively K-major: 2-D TMA boxes of [channels x 16 pixels] land in a raw ring, 256
+// convert threads split hi/lo and write 16-byte core-matrix rows (K-adjacent core matrices are placed LBO = n*128+32
+// bytes apart so the 4 k-quads of a row fall in different banks), one thread issues 12 MMAs per 16-pixel chunk.
+// A CTA accumulates a contiguous range of pixel chunks in TMEM and writes ONE partial [M][N]; a small kernel reduces
+// the partials in a fixed order (deterministic).
+constexpr int kWgtThreads = 320;      // warps 0-7 convert (+ epilogue), warp 8 MMA, warp 9 TMA issue
+constexpr int kWgtStages = 3, kWgtRaw = 2;
+__host__ __device__ inline int wgt_off_x0(int M) { return (M * kTcBK + 31) & ~31; }                 // floats, 128-byte aligned
+__host__ __device__ inline int wgt_raw_floats(int M, int K) { return (wgt_off_x0(M) + K * kTcBK + 31) & ~31; }
+
+struct WgtParams {
+  const float* x1; int C1;
+  float* part;
+  int B, M, C0, K, HW, npadN, mrows, total_chunks, per_cta;
+};
+
+__global__ void __launch_bounds__(kWgtThreads, 1)
+k_wgrad_tc(WgtParams p, const __grid_constant__ CUtensorMap tmap_g, const __grid_constant__ CUtensorMap tmap_x0) {
+  PDES_DYN_SMEM(unsigned char, smem_raw);
+  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t lbo_a = (uint32_t)(p.mrows / 8) * 128 + 32, lbo_b = (uint32_t)(p.npadN / 8) * 128 + 32;
+  const uint32_t a_blk = 4 * lbo_a, b_blk = 4 * lbo_b;
+  const uint32_t stage_bytes = 2 * a_blk + 2 * b_blk;
+  const int raw_f = wgt_raw_floats(p.M, p.K);                     // floats per raw slot
+  const int off_x0 = wgt_off_x0(p.M);
+  float* raw = reinterpret_cast<float*>(base + (size_t)kWgtStages * stage_bytes);
+  __shared__ __align__(8) unsigned long long full_bar[kWgtStages], empty_bar[kWgtStages], raw_full[kWgtRaw],
+      raw_empty[kWgtRaw], done_bar;
+  __shared__ uint32_t tmem_slot;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int cpi = p.HW / kTcBK;                                   // chunks per image
+  const int c_beg = blockIdx.x * p.per_cta;
+  const int c_end = (c_beg + p.per_cta < p.total_chunks) ? (c_beg + p.per_cta) : p.total_chunks;
+  const int nch = c_end - c_beg;
+
+  if (tid == 0) {
+    for (int i = 0; i < kWgtStages; ++i) { ptx::mbar_init(&full_bar[i], 256); ptx::mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < kWgtRaw; ++i) { ptx::mbar_init(&raw_full[i], 1); ptx::mbar_init(&raw_empty[i], 256); }
+    ptx::mbar_init(&done_bar, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 8) {
+    ptx::tmem_alloc(&tmem_slot, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp < 8) {
+    // ================================================================== convert
+    const int nitems = (p.mrows + p.npadN) * 4;
+    for (int c = 0; c < nch; ++c) {
+      const uint32_t s = c % kWgtStages, r = c % kWgtRaw;
+      if (c >= kWgtStages) ptx::mbar_wait(&empty_bar[s], ((c / kWgtStages) - 1) & 1);
+      ptx::mbar_wait(&raw_full[r], (c / kWgtRaw) & 1);
+      const float* rw = raw + (size_t)r * raw_f;
+      unsigned char* st = base + (size_t)s * stage_bytes;
+      for (int it = tid; it < nitems; it += 256) {
+        const int row = it >> 2, kq = it & 3;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        unsigned char* dst;
+        if (row < p.mrows) {                                       // A: g rows
+          if (row < p.M) v = *reinterpret_cast<const float4*>(rw + row * kTcBK + kq * 4);
+          dst = st + (uint32_t)kq * lbo_a + (uint32_t)(row >> 3) * 128 + (uint32_t)(row & 7) * 16;
+        } else {                                                   // B: input rows, then the all-ones row
+          const int n = row - p.mrows;
+          if (n < p.K) v = *reinterpret_cast<const float4*>(rw + off_x0 + n * kTcBK + kq * 4);
+          else if (n == p.K) v = make_float4(1.f, 1.f, 1.f, 1.f);
+          dst = st + 2 * a_blk + (uint32_t)kq * lbo_b + (uint32_t)(n >> 3) * 128 + (uint32_t)(n & 7) * 16;
+        }
+        float4 hi, lo;
+        hi.x = tf32_hi(v.x); lo.x = v.x - hi.x;
+        hi.y = tf32_hi(v.y); lo.y = v.y - hi.y;
+        hi.z = tf32_hi(v.z); lo.z = v.z - hi.z;
+        hi.w = tf32_hi(v.w); lo.w = v.w - hi.w;
+        *reinterpret_cast<float4*>(dst) = hi;
+        *reinterpret_cast<float4*>(dst + (row < p.mrows ? a_blk : b_blk)) = lo;
+      }
+      ptx::mbar_arrive(&raw_empty[r]);
+      ptx::fence_proxy_async();
+      ptx::mbar_arrive(&full_bar[s]);
+    }
+    // ================================================================== epilogue: one partial per CTA
+    if (nch > 0) {
+      ptx::mbar_wait(&done_bar, 0);
+      ptx::tc_fence_after();
+    }
+    const int quad = warp & 3, tile = warp >> 2;                   // warps 0-3: rows [0,128), warps 4-7: second tile
+    const int o = (tile == 0 ? 0 : p.mrows - 128) + quad * 32 + lane;
+    const bool wr = (tile == 0) ? (o < p.M) : (p.M > 128 && o >= 128 && o < p.M);
+    float* dstrow = p.part + ((size_t)blockIdx.x * p.M + (wr ? o : 0)) * p.npadN;
+    const uint32_t tb = tmem_base + (uint32_t)tile * 256 + ((uint32_t)(quad * 32) << 16);
+#pragma unroll 1
+    for (int n0 = 0; n0 < p.npadN; n0 += 8) {
+      uint32_t rr[8];
+      if (nch > 0) {
+        ptx::tmem_ld8(tb + (uint32_t)n0, rr);
+        ptx::tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) rr[e] = 0u;
+      }
+      if (wr) {
+        *reinterpret_cast<float4*>(dstrow + n0) = make_float4(__uint_as_float(rr[0]), __uint_as_float(rr[1]), __uint_as_float(rr[2]), __uint_as_float(rr[3]));
+        *reinterpret_cast<float4*>(dstrow + n0 + 4) = make_float4(__uint_as_float(rr[4]), __uint_as_float(rr[5]), __uint_as_float(rr[6]), __uint_as_float(rr[7]));
+      }
+    }
+    ptx::tc_fence_before();
+  } else if (warp == 8) {
+    if (lane == 0 && nch > 0) {
+      // ================================================================ MMA issue
+      const uint32_t idesc = ptx::idesc_tf32(128, p.npadN);
+      const uint32_t row1 = (uint32_t)((p.mrows - 128) / 8) * 128;           // byte offset of the second 128-row tile
+      const uint32_t sbase = ptx::smem_u32(base);
+      const uint64_t a_hi0 = ptx::smem_desc_noswizzle(sbase, lbo_a, 128);
+      const uint64_t a_lo0 = ptx::smem_desc_noswizzle(sbase + a_blk, lbo_a, 128);
+      const uint64_t b_hi0 = ptx::smem_desc_noswizzle(sbase + 2 * a_blk, lbo_b, 128);
+      const uint64_t b_lo0 = ptx::smem_desc_noswizzle(sbase + 2 * a_blk + b_blk, lbo_b, 128);
+      const int ntile = p.mrows > 128 ? 2 : 1;
+      for (int c = 0; c < nch; ++c) {
+        const uint32_t s = c % kWgtStages;
+        ptx::mbar_wait(&full_bar[s], (c / kWgtStages) & 1);
+        ptx::tc_fence_after();
+        const uint64_t ds = (uint64_t)((s * stage_bytes) >> 4);
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+          const uint64_t kb = ds + (uint64_t)((ks * 2 * lbo_b) >> 4);
+          for (int t = 0; t < ntile; ++t) {
+            const uint64_t ka = ds + (uint64_t)((ks * 2 * lbo_a + (t ? row1 : 0u)) >> 4);
+            const uint32_t dcol = tmem_base + (uint32_t)t * 256;
+            const uint32_t accf = (c | ks) != 0 ? 1u : 0u;
+            ptx::mma_tf32(dcol, a_lo0 + ka, b_hi0 + kb, idesc, accf);
+            ptx::mma_tf32(dcol, a_hi0 + ka, b_lo0 + kb, idesc, 1u);
+            ptx::mma_tf32(dcol, a_hi0 + ka, b_hi0 + kb, idesc, 1u);
+          }
+        }
+        ptx::tc_commit(&empty_bar[s]);
+      }
+      ptx::tc_commit(&done_bar);
+    }
+  } else if (lane == 0) {
+    // ================================================================== TMA issue
+    for (int c = 0; c < nch; ++c) {
+      const uint32_t r = c % kWgtRaw;
+      if (c >= kWgtRaw) ptx::mbar_wait(&raw_empty[r], ((c / kWgtRaw) - 1) & 1);
+      const int gc = c_beg + c;
+      const int b = gc / cpi, px = (gc - b * cpi) * kTcBK;
+      float* dst = raw + (size_t)r * raw_f;
+      ptx::mbar_arrive_expect_tx(&raw_full[r], (uint32_t)(p.M + p.K) * kTcBK * 4);
+      ptx::tma_load_2d(dst, &tmap_g, px, b * p.M, &raw_full[r]);
+      ptx::tma_load_2d(dst + off_x0, &tmap_x0, px, b * p.C0, &raw_full[r]);
+      for (int k = 0; k < p.C1; ++k)
+        ptx::bulk_g2s(dst + off_x0 + (p.C0 + k) * kTcBK, p.x1 + ((size_t)b * p.C1 + k) * p.HW + px, kTcBK * 4, &raw_full[r]);
+    }
+  }
+  __syncthreads();
+  if (warp == 8) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_wgrad_reduce_ld(const float* __restrict__ part, int nslab, int M, int K, int ld, float* __restrict__ dW,
+                  float* __restrict__ dbias) {
+  const int n = M * (K + 1);
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  const int o = idx / (K + 1), i = idx % (K + 1);
+  float sum = 0.0f;
+  for (int s = 0; s < nslab; ++s) sum += __ldg(part + ((size_t)s * M + o) * ld + i);
+  if (i < K) {
+    if (dW != nullptr) dW[(size_t)o * K + i] = sum;
+  } else if (dbias != nullptr) {
+    dbias[o] = sum;
+  }
+}
+
 #endif  // !PDES_CPU_EMU
 
 int g_tc_mode =
@@ -715,6 +901,80 @@ int pdes_inv_w_gemm_tc_ok(int N, int K, int H, int W, int m2, const float* x0, c
   const int rows = (pdes::kTcM + W - 1) / W + 1;
   if (m2 > 0 && rows * 2 * m2 > 8 * pdes::kTcBK) return 0;
   return 1;
+}
+
+size_t pdes_wgrad_tc_workspace_floats(int M, int K) {
+  if (M <= 0 || K <= 0 || M > 256 || K + 1 > 256) return 0;
+  return (size_t)pdes::kWgtMaxCtas * M * pdes::tc_npad(K + 1);
+}
+
+/* dW / dbias of the 1x1 conv on tcgen05 (3xTF32).  Returns PDES_ERR_UNSUPPORTED when the shape does not fit the
+ * tensor-core kernel (the caller then uses pdes_wgrad). */
+int pdes_wgrad_tc(const float* g, const float* x0, int C0, const float* x1, int C1, float* dW, float* dbias, float* ws,
+                  int B, int M, int HW, void* stream) {
+  using namespace pdes;
+#ifdef PDES_CPU_EMU
+  (void)g; (void)x0; (void)C0; (void)x1; (void)C1; (void)dW; (void)dbias; (void)ws; (void)B; (void)M; (void)HW; (void)stream;
+  set_error("pdes_wgrad_tc: tcgen05 path is not available in the CPU emulation build");
+  return PDES_ERR_UNSUPPORTED;
+#else
+  PDES_REQUIRE(g && x0 && ws, PDES_ERR_ARG, "pdes_wgrad_tc: null pointer");
+  const int K = C0 + C1;
+  const bool ok = B > 0 && M >= 8 && M <= 256 && C0 >= 1 && C0 <= 256 && C1 >= 0 && K + 1 <= 256 && HW % kTcBK == 0 &&
+                  aligned16(g) && aligned16(x0) && (x1 == nullptr || aligned16(x1)) && (C1 == 0) == (x1 == nullptr) &&
+                  g_encode_tiled() != nullptr;
+  PDES_REQUIRE(ok, PDES_ERR_UNSUPPORTED, "pdes_wgrad_tc: shape not supported by the tensor-core kernel");
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  WgtParams p;
+  p.x1 = x1; p.C1 = C1; p.part = ws; p.B = B; p.M = M; p.C0 = C0; p.K = K; p.HW = HW;
+  p.npadN = tc_npad(K + 1);
+  const int mpad = (M + 7) & ~7;
+  p.mrows = mpad > 128 ? mpad : 128;
+  p.total_chunks = B * (HW / kTcBK);
+  int G = g_num_sms < kWgtMaxCtas ? g_num_sms : kWgtMaxCtas;
+  if (G > p.total_chunks) G = p.total_chunks;
+  p.per_cta = ceil_div(p.total_chunks, G);
+  G = ceil_div(p.total_chunks, p.per_cta);
+  const uint32_t lbo_a = (uint32_t)(p.mrows / 8) * 128 + 32, lbo_b = (uint32_t)(p.npadN / 8) * 128 + 32;
+  const size_t smem = (size_t)kWgtStages * 8 * (lbo_a + lbo_b) + (size_t)kWgtRaw * wgt_raw_floats(M, K) * 4 + 1024;
+  PDES_REQUIRE(smem <= 227 * 1024, PDES_ERR_UNSUPPORTED, "pdes_wgrad_tc: needs %zu B of shared memory", smem);
+  alignas(64) CUtensorMap tg, tx;
+  memset(&tg, 0, sizeof(tg));
+  memset(&tx, 0, sizeof(tx));
+  {
+    const cuuint64_t gdim[2] = {(cuuint64_t)HW, (cuuint64_t)B * (cuuint64_t)M};
+    const cuuint64_t gstr[1] = {(cuuint64_t)HW * 4};
+    const cuuint32_t box[2] = {(cuuint32_t)kTcBK, (cuuint32_t)M};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = g_encode_tiled()(&tg, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(g), gdim, gstr, box, estr,
+                                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    PDES_REQUIRE(r == CUDA_SUCCESS, PDES_ERR_UNSUPPORTED, "pdes_wgrad_tc: cuTensorMapEncodeTiled(g) failed (%d)", (int)r);
+  }
+  {
+    const cuuint64_t gdim[2] = {(cuuint64_t)HW, (cuuint64_t)B * (cuuint64_t)C0};
+    const cuuint64_t gstr[1] = {(cuuint64_t)HW * 4};
+    const cuuint32_t box[2] = {(cuuint32_t)kTcBK, (cuuint32_t)C0};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = g_encode_tiled()(&tx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(x0), gdim, gstr, box, estr,
+                                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    PDES_REQUIRE(r == CUDA_SUCCESS, PDES_ERR_UNSUPPORTED, "pdes_wgrad_tc: cuTensorMapEncodeTiled(x0) failed (%d)", (int)r);
+  }
+  auto kfn = k_wgrad_tc;
+  PDES_SET_SMEM(kfn, smem);
+  PDES_LAUNCH(kfn, dim3((unsigned)G), dim3(kWgtThreads), smem, stream, p, tg, tx);
+  if (int e = check_launch("pdes_wgrad_tc")) return e;
+  auto rfn = k_wgrad_reduce_ld;
+  const int n = M * (K + 1);
+  PDES_LAUNCH(rfn, dim3((unsigned)ceil_div(n, 256)), dim3(256), 0, stream, ws, G, M, K, p.npadN, dW, dbias);
+  return check_launch("pdes_wgrad_tc_reduce");
+#endif
 }
 
 size_t pdes_gemm_tc_pack_floats(int K, int N) {

@@ -336,3 +336,28 @@ def check_groupnorm(be, B=3, C=12, HW=35, G=4, act=1):
     for k, v in errs.items():
         assert v < TOL, f"groupnorm {k}: {v:.3e}"
     return errs
+
+
+def check_wgrad_tc(be, shape):
+    """tcgen05 weight/bias gradient against the float64 oracle (returns None when the shape stays on the FFMA kernel)."""
+    B, C0, C1, Cout, H, W, m1, m2 = shape
+    Cin = C0 + C1
+    rng = _rng(4)
+    g = rng.standard_normal((B, Cout, H, W)).astype(np.float32)
+    x0 = rng.standard_normal((B, C0, H, W)).astype(np.float32)
+    x1 = rng.standard_normal((B, C1, H, W)).astype(np.float32) if C1 else None
+    dg, dx0, dx1 = be.upload(g), be.upload(x0), (be.upload(x1) if C1 else None)
+    nws = be.lib.pdes_wgrad_tc_workspace_floats(Cout, Cin)
+    if nws == 0:
+        return None
+    ws = be.empty((nws,))
+    dW = be.empty((Cout, Cin)); db = be.empty((Cout,))
+    rc = be.lib.pdes_wgrad_tc(be.ptr(dg), be.ptr(dx0), C0, be.ptr(dx1), C1, be.ptr(dW), be.ptr(db), be.ptr(ws), B, Cout, H * W, be.stream)
+    if rc == 2:
+        return None
+    be.check(rc)
+    xin = x0 if x1 is None else np.concatenate([x0, x1], axis=1)
+    e2 = so.rel_l2(be.download(dW), np.einsum("bohw,bihw->oi", g.astype(np.float64), xin))
+    e3 = so.rel_l2(be.download(db), g.astype(np.float64).sum(axis=(0, 2, 3)))
+    assert e2 < TOL and e3 < TOL, f"wgrad_tc {shape}: dW {e2:.3e} dbias {e3:.3e}"
+    return e2, e3

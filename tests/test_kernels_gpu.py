@@ -107,3 +107,13 @@ def test_groupnorm_act(be):
     kc.check_groupnorm(be, B=3, C=12, HW=35, G=4, act=1)
     kc.check_groupnorm(be, B=2, C=193, HW=96 * 64, G=1, act=1)     # the U-Net residual-block shape
     kc.check_groupnorm(be, B=2, C=192, HW=100 * 68, G=8, act=1)    # the final norm of the U-Net
+
+
+@pytest.mark.parametrize("shape", TC_SHAPES)
+def test_tc_wgrad(be, shape):
+    kc.check_wgrad_tc(be, shape)
+
+
+def test_tc_wgrad_path_is_taken_for_config_shapes(be):
+    for shape in FULL_SHAPES + [(2, 20, 1, 24, 8, 24, 3, 4), (1, 40, 0, 200, 16, 32, 5, 7)]:
+        assert kc.check_wgrad_tc(be, shape) is not None

@@ -75,6 +75,7 @@ def main():
         gw1, gw2 = torch.empty_like(w1), torch.empty_like(w2)
         dwc, dbias = torch.empty_like(wc), torch.empty_like(bias)
         GO = torch.empty(B, Cout, 2 * m1, m2, dtype=torch.complex64, device=dev)
+        wgtc = torch.empty(lib.pdes_wgrad_tc_workspace_floats(Cout, Cin), device=dev)
         wgws = torch.empty(lib.pdes_wgrad_workspace_floats(B, Cout, Cin, HW), device=dev)
         p = lambda t: t.data_ptr()
         ck = lambda c: _native.check(lib, c)
@@ -100,6 +101,8 @@ def main():
                        16 * Cin * Cout * MM),
             "wgrad": (lambda: ck(lib.pdes_wgrad(p(g), p(h), C0, p(vb), C1, p(dwc), p(dbias), p(wgws), B, Cout, HW, st)),
                       4 * B * (Cin + Cout) * HW),
+            "wgrad_tcgen05": (lambda: ck(lib.pdes_wgrad_tc(p(g), p(h), C0, p(vb), C1, p(dwc), p(dbias), p(wgtc), B, Cout, HW, st)),
+                              4 * B * (Cin + Cout) * HW),
             "block_backward": (lambda: ck(lib.pdes_block_backward(p(g), p(pre), p(h), C0, p(vb), C1, p(X), p(w1), p(w2), p(wc),
                                                                   p(tab), p(wsb), p(gpre), p(dh), p(gw1), p(gw2), p(dwc), p(dbias),
                                                                   B, Cout, H, W, m1, m2, 1, st)),
