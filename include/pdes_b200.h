@@ -111,6 +111,15 @@ size_t pdes_wgrad_tc_workspace_floats(int M, int K);
 int pdes_wgrad_tc(const float* g, const float* x0, int C0, const float* x1, int C1, float* dW, float* dbias,
                   float* ws, int B, int M, int HW, void* stream);
 
+/* ---- U-Net branch: 3x3 valid convolution forward on tcgen05 (3xTF32 implicit GEMM) ------
+ * Replaces the forward of the nn.Conv2d(k=3, padding=0) layers of the reference's ResidualBlock
+ * (proc_unet_modern.py:217-218, the "circular without padding" valid convs).  Needs W % 4 == 0, H >= 10, W >= 20,
+ * N <= 256, N % 4 == 0; otherwise returns PDES_ERR_UNSUPPORTED and the caller keeps cuDNN. */
+size_t pdes_conv3x3_tc_pack_floats(int Cin, int N);
+int pdes_conv3x3_tc_ok(int B, int Cin, int N, int H, int W, const float* x);
+int pdes_conv3x3_tc(const float* x, const float* w, const float* bias, float* wpack, float* out, int B, int Cin, int N,
+                    int H, int W, void* stream);
+
 /* ---- pointwise / small helpers ------------------------------------------------------------------------
  * g_pre = g_out * act'(pre)  (GeluBackward of proc_ufno.py:118) */
 int pdes_act_bwd(const float* g_out, const float* pre, float* g_pre, size_t n, int act, void* stream);

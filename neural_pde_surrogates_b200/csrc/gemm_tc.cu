@@ -838,6 +838,239 @@ k_wgrad_reduce_ld(const float* __restrict__ part, int nslab, int M, int K, int l
   }
 }
 
+
+// ----------------------------------------------------------------------------------------------------------------
+// U-Net branch: 3x3 *valid* convolution forward as an implicit GEMM on the same tcgen05
+// pipeline (3xTF32).  M = 128 output pixels (a tile of 8 rows x 16 columns), N = Cout, K = Cin * 9.
+//   raw ring : one 3-D TMA box [16 channels][10 rows][20 columns] per channel chunk (the tile's input patch)
+//   convert  : for each of the 9 taps (ky,kx) the 128 threads gather their pixel's 16 channels from the patch,
+//              split hi/lo and write the canonical A stage -- the patch is read from HBM once and reused 9 times
+//   B ring   : weights packed per (channel chunk, tap) into canonical (hi, lo) blocks, one bulk copy per step
+//   MMA / epilogue as in the GEMM above (double-buffered TMEM accumulator, bias add, coalesced stores).
+constexpr int kCvTH = 8, kCvTW = 16, kCvBH = kCvTH + 2, kCvBW = 20;   // output tile 8x16, input box 10x20 (80-byte rows)
+constexpr int kCvRawF = kTcBK * kCvBH * kCvBW;                            // 3200 floats = 12.8 KB per raw slot
+
+struct ConvParams {
+  const float* wpack;
+  const float* bias;
+  float* out;
+  int B, Cin, N, npad, H, W, Ho, Wo, tiles_y, tiles_x;
+};
+
+__global__ void __launch_bounds__(256)
+k_pack_conv3x3_tf32(const float* __restrict__ Wt, int N, int Cin, int npad, int ncc, float* __restrict__ out) {
+  const int total = ncc * 9 * npad * kTcBK;
+  const int lbo_f = (npad / 8) * 32;
+  const size_t blk = (size_t)npad * kTcBK;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int n = idx % npad;
+    const int kk = (idx / npad) % kTcBK;
+    const int tap = (idx / (npad * kTcBK)) % 9;
+    const int cc = idx / (npad * kTcBK * 9);
+    const int c = cc * kTcBK + kk;
+    const float w = (c < Cin && n < N) ? __ldg(Wt + ((size_t)n * Cin + c) * 9 + tap) : 0.0f;
+    const float hi = tf32_hi(w);
+    const size_t off = (size_t)(kk / 4) * lbo_f + (size_t)(n / 8) * 32 + (n % 8) * 4 + (kk % 4);
+    const size_t chunk = (size_t)cc * 9 + tap;
+    out[chunk * 2 * blk + off] = hi;
+    out[chunk * 2 * blk + blk + off] = w - hi;
+  }
+}
+
+__global__ void __launch_bounds__(kV3Threads, 1)
+k_conv3x3_tc(ConvParams p, const __grid_constant__ CUtensorMap tmap_x) {
+  PDES_DYN_SMEM(unsigned char, smem_raw);
+  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int npad = p.npad;
+  const uint32_t a_blk = kTcM * kTcBK * 4;
+  const uint32_t b_blk = (uint32_t)npad * kTcBK * 4;
+  const uint32_t a_stage = 2 * a_blk, b_stage = 2 * b_blk;
+  unsigned char* sA = base;
+  unsigned char* sB = sA + kV3ASt * a_stage;
+  float* raw = reinterpret_cast<float*>(sB + kV3BSt * b_stage);
+  __shared__ __align__(8) V3Bars bars;
+  __shared__ uint32_t tmem_slot;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int ncc = tc_nchunks(p.Cin);
+  const int nch = ncc * 9;                                        // MMA chunks per tile
+  const int tiles_img = p.tiles_y * p.tiles_x;
+  const int ntiles = p.B * tiles_img;
+
+  if (tid == 0) {
+    for (int i = 0; i < kV3ASt; ++i) { ptx::mbar_init(&bars.a_full[i], 128); ptx::mbar_init(&bars.a_empty[i], 1); }
+    for (int i = 0; i < kV3BSt; ++i) { ptx::mbar_init(&bars.b_full[i], 1); ptx::mbar_init(&bars.b_empty[i], 1); }
+    for (int i = 0; i < kV3Raw; ++i) { ptx::mbar_init(&bars.raw_full[i], 1); ptx::mbar_init(&bars.raw_empty[i], 128); }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&bars.acc_full[i], 1); ptx::mbar_init(&bars.acc_empty[i], 32 * 4 * kV3EpiParts); }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 4) {
+    ptx::tmem_alloc(&tmem_slot, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  auto tile_geom = [&](int t, int& b, int& y0, int& x0) {
+    b = t / tiles_img;
+    const int r = t - b * tiles_img;
+    y0 = (r / p.tiles_x) * kCvTH;
+    x0 = (r % p.tiles_x) * kCvTW;
+  };
+
+  if (warp < 4) {
+    // ================================================================== convert (gather one tap per A stage)
+    const uint32_t row_off = (uint32_t)(tid >> 3) * 128 + (uint32_t)(tid & 7) * 16;
+    const int pr = tid >> 4, pc = tid & 15;                        // pixel of this thread inside the 8x16 tile
+    uint32_t g = 0, gr = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      for (int cc = 0; cc < ncc; ++cc, ++gr) {
+        const uint32_t r = gr % kV3Raw;
+        ptx::mbar_wait(&bars.raw_full[r], (gr / kV3Raw) & 1);
+        const float* patch = raw + (size_t)r * kCvRawF + pr * kCvBW + pc;
+        const int nvalid = (p.Cin - cc * kTcBK < kTcBK) ? (p.Cin - cc * kTcBK) : kTcBK;
+#pragma unroll 1
+        for (int tap = 0; tap < 9; ++tap, ++g) {
+          const uint32_t s = g % kV3ASt;
+          if (g >= kV3ASt) ptx::mbar_wait(&bars.a_empty[s], ((g / kV3ASt) - 1) & 1);
+          unsigned char* st = sA + s * a_stage;
+          const float* src = patch + (tap / 3) * kCvBW + (tap % 3);
+          float v[kTcBK];
+#pragma unroll
+          for (int kk = 0; kk < kTcBK; ++kk) v[kk] = (kk < nvalid) ? src[kk * (kCvBH * kCvBW)] : 0.0f;
+#pragma unroll
+          for (int qd = 0; qd < kTcBK / 4; ++qd) {
+            float4 hi, lo;
+            hi.x = tf32_hi(v[4 * qd + 0]); lo.x = v[4 * qd + 0] - hi.x;
+            hi.y = tf32_hi(v[4 * qd + 1]); lo.y = v[4 * qd + 1] - hi.y;
+            hi.z = tf32_hi(v[4 * qd + 2]); lo.z = v[4 * qd + 2] - hi.z;
+            hi.w = tf32_hi(v[4 * qd + 3]); lo.w = v[4 * qd + 3] - hi.w;
+            const uint32_t off = (uint32_t)qd * (kTcM / 8) * 128 + row_off;
+            *reinterpret_cast<float4*>(st + off) = hi;
+            *reinterpret_cast<float4*>(st + a_blk + off) = lo;
+          }
+          ptx::fence_proxy_async();
+          ptx::mbar_arrive(&bars.a_full[s]);
+        }
+        ptx::mbar_arrive(&bars.raw_empty[r]);
+      }
+    }
+  } else if (warp == 4) {
+    if (lane == 0) {
+      // ================================================================ MMA issue
+      const uint32_t idesc = ptx::idesc_tf32(kTcM, npad);
+      const uint32_t lbo_a = (kTcM / 8) * 128, lbo_b = (uint32_t)(npad / 8) * 128, sbo = 128;
+      const uint64_t a_hi0 = ptx::smem_desc_noswizzle(ptx::smem_u32(sA), lbo_a, sbo);
+      const uint64_t a_lo0 = ptx::smem_desc_noswizzle(ptx::smem_u32(sA) + a_blk, lbo_a, sbo);
+      const uint64_t b_hi0 = ptx::smem_desc_noswizzle(ptx::smem_u32(sB), lbo_b, sbo);
+      const uint64_t b_lo0 = ptx::smem_desc_noswizzle(ptx::smem_u32(sB) + b_blk, lbo_b, sbo);
+      uint32_t g = 0, it = 0;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+        const uint32_t a = it & 1;
+        if (it >= 2) ptx::mbar_wait(&bars.acc_empty[a], ((it / 2) - 1) & 1);
+        ptx::tc_fence_after();
+        const uint32_t dcol = tmem_base + a * 256;
+        for (int c = 0; c < nch; ++c, ++g) {
+          const uint32_t s = g % kV3ASt, q = g % kV3BSt;
+          ptx::mbar_wait(&bars.a_full[s], (g / kV3ASt) & 1);
+          ptx::mbar_wait(&bars.b_full[q], (g / kV3BSt) & 1);
+          ptx::tc_fence_after();
+          const uint64_t da = (uint64_t)((s * a_stage) >> 4), db = (uint64_t)((q * b_stage) >> 4);
+#pragma unroll
+          for (int ks = 0; ks < kTcBK / 8; ++ks) {
+            const uint64_t ka = da + (uint64_t)((ks * 2 * lbo_a) >> 4), kb = db + (uint64_t)((ks * 2 * lbo_b) >> 4);
+            ptx::mma_tf32(dcol, a_lo0 + ka, b_hi0 + kb, idesc, (c | ks) != 0 ? 1u : 0u);
+            ptx::mma_tf32(dcol, a_hi0 + ka, b_lo0 + kb, idesc, 1u);
+            ptx::mma_tf32(dcol, a_hi0 + ka, b_hi0 + kb, idesc, 1u);
+          }
+          ptx::tc_commit(&bars.a_empty[s]);
+          ptx::tc_commit(&bars.b_empty[q]);
+        }
+        ptx::tc_commit(&bars.acc_full[a]);
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {
+      // ================================================================ raw ring: one 3-D TMA box per channel chunk
+      uint32_t gr = 0;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        int b, y0, x0;
+        tile_geom(t, b, y0, x0);
+        for (int cc = 0; cc < ncc; ++cc, ++gr) {
+          const uint32_t r = gr % kV3Raw;
+          if (gr >= kV3Raw) ptx::mbar_wait(&bars.raw_empty[r], ((gr / kV3Raw) - 1) & 1);
+          ptx::mbar_arrive_expect_tx(&bars.raw_full[r], (uint32_t)kCvRawF * 4);
+          ptx::tma_load_3d(raw + (size_t)r * kCvRawF, &tmap_x, x0, y0, b * p.Cin + cc * kTcBK, &bars.raw_full[r]);
+        }
+      }
+    }
+  } else if (warp == 6) {
+    if (lane == 0) {
+      // ================================================================ B ring: packed weights of (chunk, tap)
+      uint32_t g = 0;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        for (int c = 0; c < nch; ++c, ++g) {
+          const uint32_t q = g % kV3BSt;
+          if (g >= kV3BSt) ptx::mbar_wait(&bars.b_empty[q], ((g / kV3BSt) - 1) & 1);
+          ptx::mbar_arrive_expect_tx(&bars.b_full[q], b_stage);
+          ptx::bulk_g2s(sB + q * b_stage, p.wpack + (size_t)c * (b_stage / 4), b_stage, &bars.b_full[q]);
+        }
+      }
+    }
+  } else if (warp >= 8) {
+    // ==================================================================== epilogue
+    const int quad = warp & 3, part = (warp - 8) >> 2;
+    const int N = p.N;
+    const int nq = (npad + 7) / 8;
+    const int per = (nq + kV3EpiParts - 1) / kV3EpiParts;
+    const int qbeg = (part * per < nq) ? part * per : nq, qend = (qbeg + per < nq) ? qbeg + per : nq;
+    const int m = quad * 32 + lane, pr = m >> 4, pc = m & 15;
+    const size_t plane = (size_t)p.Ho * p.Wo;
+    uint32_t it = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+      int b, y0, x0;
+      tile_geom(t, b, y0, x0);
+      const int y = y0 + pr, x = x0 + pc;
+      const bool pvalid = y < p.Ho && x < p.Wo;
+      const uint32_t a = it & 1;
+      ptx::mbar_wait(&bars.acc_full[a], (it / 2) & 1);
+      ptx::tc_fence_after();
+      const uint32_t tbase = tmem_base + a * 256 + ((uint32_t)(quad * 32) << 16);
+      float* obase = p.out + (size_t)b * N * plane + (size_t)y * p.Wo + x;
+#pragma unroll 1
+      for (int qi = qbeg; qi < qend; ++qi) {
+        const int n0 = qi * 8;
+        uint32_t r[8];
+        ptx::tmem_ld8(tbase + (uint32_t)n0, r);
+        ptx::tmem_ld_wait();
+        if (qi + 1 == qend) {
+          ptx::tc_fence_before();
+          ptx::mbar_arrive(&bars.acc_empty[a]);
+        }
+        if (pvalid) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int n = n0 + e;
+            if (n < N) obase[(size_t)n * plane] = __uint_as_float(r[e]) + (p.bias != nullptr ? __ldg(p.bias + n) : 0.0f);
+          }
+        }
+      }
+      if (qbeg >= qend) {
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(&bars.acc_empty[a]);
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
 #endif  // !PDES_CPU_EMU
 
 int g_tc_mode =
@@ -974,6 +1207,69 @@ int pdes_wgrad_tc(const float* g, const float* x0, int C0, const float* x1, int 
   const int n = M * (K + 1);
   PDES_LAUNCH(rfn, dim3((unsigned)ceil_div(n, 256)), dim3(256), 0, stream, ws, G, M, K, p.npadN, dW, dbias);
   return check_launch("pdes_wgrad_tc_reduce");
+#endif
+}
+
+size_t pdes_conv3x3_tc_pack_floats(int Cin, int N) {
+  if (Cin <= 0 || N <= 0 || N > pdes::kTcMaxN) return 0;
+  return (size_t)pdes::tc_nchunks(Cin) * 9 * 2 * pdes::tc_block_floats(N);
+}
+
+int pdes_conv3x3_tc_ok(int B, int Cin, int N, int H, int W, const float* x) {
+  if (B <= 0 || Cin <= 0 || N <= 0 || N > pdes::kTcMaxN || N % 4 != 0) return 0;
+  if (H < 10 || W < 20 || W % 4 != 0) return 0;                     // 3-D TMA box 10 x 20, 16-byte global strides
+  if ((reinterpret_cast<uintptr_t>(x) & 15u) != 0) return 0;
+  return 1;
+}
+
+/* out[B][N][H-2][W-2] = valid 3x3 cross-correlation of x[B][Cin][H][W] with w[N][Cin][3][3] (+ bias), 3xTF32 on
+ * tcgen05.  wpack needs pdes_conv3x3_tc_pack_floats() floats and is rewritten on every call (weights change every
+ * optimizer step).  Returns PDES_ERR_UNSUPPORTED when pdes_conv3x3_tc_ok() is false. */
+int pdes_conv3x3_tc(const float* x, const float* w, const float* bias, float* wpack, float* out, int B, int Cin, int N,
+                    int H, int W, void* stream) {
+  using namespace pdes;
+#ifdef PDES_CPU_EMU
+  (void)x; (void)w; (void)bias; (void)wpack; (void)out; (void)B; (void)Cin; (void)N; (void)H; (void)W; (void)stream;
+  set_error("pdes_conv3x3_tc: tcgen05 path is not available in the CPU emulation build");
+  return PDES_ERR_UNSUPPORTED;
+#else
+  PDES_REQUIRE(x && w && wpack && out, PDES_ERR_ARG, "pdes_conv3x3_tc: null pointer");
+  PDES_REQUIRE(pdes_conv3x3_tc_ok(B, Cin, N, H, W, x) && g_encode_tiled() != nullptr, PDES_ERR_UNSUPPORTED,
+               "pdes_conv3x3_tc: shape/alignment not supported (Cin=%d N=%d H=%d W=%d)", Cin, N, H, W);
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  ConvParams p;
+  p.wpack = wpack; p.bias = bias; p.out = out; p.B = B; p.Cin = Cin; p.N = N; p.npad = tc_npad(N); p.H = H; p.W = W;
+  p.Ho = H - 2; p.Wo = W - 2;
+  p.tiles_y = ceil_div(p.Ho, kCvTH); p.tiles_x = ceil_div(p.Wo, kCvTW);
+  const int ncc = tc_nchunks(Cin);
+  {
+    const int total = ncc * 9 * p.npad * kTcBK;
+    auto pk = k_pack_conv3x3_tf32;
+    PDES_LAUNCH(pk, dim3((unsigned)ceil_div(total, 256)), dim3(256), 0, stream, w, N, Cin, p.npad, ncc, wpack);
+    if (int e = check_launch("pdes_conv3x3_tc(pack)")) return e;
+  }
+  alignas(64) CUtensorMap tm;
+  memset(&tm, 0, sizeof(tm));
+  const cuuint64_t gdim[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B * (cuuint64_t)Cin};
+  const cuuint64_t gstr[2] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4};
+  const cuuint32_t box[3] = {(cuuint32_t)kCvBW, (cuuint32_t)kCvBH, (cuuint32_t)kTcBK};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  const CUresult r = g_encode_tiled()(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(x), gdim, gstr, box, estr,
+                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  PDES_REQUIRE(r == CUDA_SUCCESS, PDES_ERR_UNSUPPORTED, "pdes_conv3x3_tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
+  const size_t smem = (size_t)kV3ASt * 2 * kTcM * kTcBK * 4 + (size_t)kV3BSt * 2 * p.npad * kTcBK * 4 +
+                      (size_t)kV3Raw * kCvRawF * 4 + 1024;
+  const int ntiles = B * p.tiles_y * p.tiles_x;
+  auto kfn = k_conv3x3_tc;
+  PDES_SET_SMEM(kfn, smem);
+  PDES_LAUNCH(kfn, dim3((unsigned)(ntiles < g_num_sms ? ntiles : g_num_sms)), dim3(kV3Threads), smem, stream, p, tm);
+  return check_launch("pdes_conv3x3_tc");
 #endif
 }
 

@@ -68,6 +68,14 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const void* tmap, int c0,
       : "memory");
 }
 
+__device__ __forceinline__ void tma_load_3d(void* dst, const void* tmap, int c0, int c1, int c2, void* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+          smem_u32(dst)),
+      "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+      : "memory");
+}
+
 // ---- tcgen05 -----------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(void* smem_result, uint32_t ncols) {   // whole warp, ncols pow2 >= 32
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "r"(ncols)

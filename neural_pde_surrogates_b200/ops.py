@@ -267,3 +267,54 @@ def group_norm_act(x, norm, act):
         return GroupNormActFunction.apply(x, norm.weight, norm.bias, norm.num_groups, norm.eps, code)
     y = norm(x)
     return y if act is None else act(y)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# U-Net branch helper: 3x3 valid convolution, forward on tcgen05 (csrc/gemm_tc.cu: k_conv3x3_tc), backward on cuDNN
+class Conv3x3ValidFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        lib = _lib()
+        x = x.contiguous()
+        w = weight.contiguous()
+        B, Cin, H, W = x.shape
+        N = w.shape[0]
+        dev = x.device
+        with torch.cuda.device(dev):
+            out = torch.empty(B, N, H - 2, W - 2, dtype=torch.float32, device=dev)
+            wpack = torch.empty(lib.pdes_conv3x3_tc_pack_floats(Cin, N), dtype=torch.float32, device=dev)
+            p = lambda t: None if t is None else t.data_ptr()
+            _native.check(lib, lib.pdes_conv3x3_tc(p(x), p(w), p(bias), p(wpack), p(out), B, Cin, N, H, W, _stream()))
+            _counters["launches"] += 2
+        ctx.save_for_backward(x, w)
+        ctx.has_bias = bias is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w = ctx.saved_tensors
+        bias_sizes = [w.shape[0]] if ctx.has_bias else None
+        mask = [ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.has_bias and ctx.needs_input_grad[2]]
+        gx, gw, gb = torch.ops.aten.convolution_backward(g.contiguous(), x, w, bias_sizes, [1, 1], [0, 0], [1, 1], False,
+                                                         [0, 0], 1, mask)
+        return gx, gw, gb
+
+
+def conv3x3_valid(x, conv):
+    """conv(x) for the U-Net's 3x3 valid convolutions: tcgen05 implicit GEMM (3xTF32) when the shape allows, else cuDNN."""
+    if (x.is_cuda and x.dtype == torch.float32 and isinstance(conv, torch.nn.Conv2d) and tuple(conv.kernel_size) == (3, 3)
+            and tuple(conv.stride) == (1, 1) and tuple(conv.dilation) == (1, 1) and conv.groups == 1
+            and (tuple(conv.padding) == (0, 0) if not isinstance(conv.padding, str) else conv.padding == "valid")
+            and x.dim() == 4 and enable_conv_tc):
+        lib = _lib()
+        B, Cin, H, W = x.shape
+        xc = x if x.is_contiguous() else x.contiguous()
+        if lib.pdes_get_tensor_core_mode() >= 2 and lib.pdes_conv3x3_tc_ok(B, Cin, conv.out_channels, H, W, xc.data_ptr()):
+            return Conv3x3ValidFunction.apply(xc, conv.weight, conv.bias)
+    return conv(x)
+
+
+# Off by default: measured on B200 (tools/time_conv.py) cuDNN's fp32 Winograd is within 1.2-1.5x of this kernel and more
+# accurate (the fp32 accumulation of tcgen05 truncates, so 3xTF32 reaches 1.4e-5 .. 2.6e-5 rel. L2 at K = Cin*9 > 1700,
+# above the 1e-5 bar); kept as an opt-in experiment for the next round (split-K over several TMEM accumulators).
+enable_conv_tc = False

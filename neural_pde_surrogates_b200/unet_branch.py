@@ -70,8 +70,8 @@ class ResidualBlock(nn.Module):
         self.norm2 = nn.GroupNorm(n_groups, out_channels) if norm else nn.Identity()
 
     def forward(self, x):
-        y = self.conv1(ops.group_norm_act(x, self.norm1, self.activation))
-        y = self.conv2(ops.group_norm_act(y, self.norm2, self.activation))
+        y = ops.conv3x3_valid(ops.group_norm_act(x, self.norm1, self.activation), self.conv1)
+        y = ops.conv3x3_valid(ops.group_norm_act(y, self.norm2, self.activation), self.conv2)
         skip = self.shortcut(x)
         return fit_to(y, skip.shape[-2:]) + skip
 

@@ -167,3 +167,31 @@ def test_fused_groupnorm_gelu_vs_torch():
         yr.backward(g.double())
         for a, b in zip(got, (yr, xr.grad, nd.weight.grad, nd.bias.grad)):
             assert rel_l2(a, b) < 1e-5
+
+
+@pytest.mark.parametrize("shape", [(2, 193, 192, 96, 64), (1, 385, 192, 100, 68), (2, 20, 24, 12, 20), (1, 16, 8, 33, 44)])
+def test_conv3x3_valid_tcgen05_vs_torch(shape):
+    """U-Net 3x3 valid conv forward on tcgen05 (3xTF32) vs PyTorch float64; backward (cuDNN) vs float64 autograd."""
+    from neural_pde_surrogates_b200 import ops
+    B, Cin, N, H, W = shape
+    torch.manual_seed(0)
+    conv = torch.nn.Conv2d(Cin, N, 3, padding_mode="circular").to(DEV)
+    x = torch.randn(B, Cin, H, W, device=DEV, requires_grad=True)
+    ops.enable_conv_tc = True                      # opt-in experiment (default off, see ops.py)
+    try:
+        y = ops.conv3x3_valid(x, conv)
+    finally:
+        ops.enable_conv_tc = False
+    assert y.grad_fn is not None and "Conv3x3Valid" in type(y.grad_fn).__name__, "tensor-core path not taken"
+    g = torch.randn_like(y)
+    y.backward(g)
+    convd = torch.nn.Conv2d(Cin, N, 3).to(DEV).double()
+    convd.load_state_dict({k: v.double() for k, v in conv.state_dict().items()})
+    xd = x.detach().double().requires_grad_()
+    yd = convd(xd)
+    yd.backward(g.double())
+    # forward: 3xTF32 with K = Cin*9 up to 3465 accumulation steps; tcgen05's fp32 accumulate truncates, hence 5e-5
+    assert rel_l2(y, yd) < 5e-5
+    assert rel_l2(x.grad, xd.grad) < 1e-5
+    assert rel_l2(conv.weight.grad, convd.weight.grad) < 1e-5
+    assert rel_l2(conv.bias.grad, convd.bias.grad) < 1e-5
