@@ -79,6 +79,8 @@ k_inv_h(const float2* __restrict__ P, int nsplit, int B, int C, int H, int m1, i
       // inside each half, so no integer division in the loop (only at k = 0 and k = m1)
       const unsigned h0m = (unsigned)(hbase + hg) % (unsigned)H, s32 = (unsigned)kIhHG % (unsigned)H;
       unsigned j0 = 0, step = 0;
+      const bool full = l0 + LCH <= m2;
+      const float2* orow = Os + (size_t)l0 * kIhLd + ot;
       for (int k = 0; k < K; ++k) {
         if (k == m1) {
           const unsigned kx = (unsigned)kx_of(k, m1, H);
@@ -97,18 +99,30 @@ k_inv_h(const float2* __restrict__ P, int nsplit, int B, int C, int H, int m1, i
         if (j0 >= (unsigned)H) j0 -= (unsigned)H;
         step += s32;
         if (step >= (unsigned)H) step -= (unsigned)H;
-        const float2* orow = Os + (size_t)(k * m2 + l0) * kIhLd + ot;
+        if (full) {                                        // all LCH columns valid: no per-column guards
 #pragma unroll
-        for (int q = 0; q < LCH; ++q) {
-          if (l0 + q < m2) {
-            const float2 o = orow[(size_t)q * kIhLd];
+          for (int q = 0; q < LCH; ++q) {
+            const float2 o = orow[q * kIhLd];
 #pragma unroll
             for (int i = 0; i < HT; ++i) {
               ar[q][i] = fmaf(o.x, t[i].x, fmaf(-o.y, t[i].y, ar[q][i]));
               ai[q][i] = fmaf(o.x, t[i].y, fmaf(o.y, t[i].x, ai[q][i]));
             }
           }
+        } else {
+#pragma unroll
+          for (int q = 0; q < LCH; ++q) {
+            if (l0 + q < m2) {
+              const float2 o = orow[q * kIhLd];
+#pragma unroll
+              for (int i = 0; i < HT; ++i) {
+                ar[q][i] = fmaf(o.x, t[i].x, fmaf(-o.y, t[i].y, ar[q][i]));
+                ai[q][i] = fmaf(o.x, t[i].y, fmaf(o.y, t[i].x, ai[q][i]));
+              }
+            }
+          }
         }
+        orow += m2 * kIhLd;
       }
       if (cvalid) {
 #pragma unroll
