@@ -326,6 +326,12 @@ struct V3Bars {
       raw_empty[kV3Raw], acc_full[2], acc_empty[2];
 };
 
+// kTA: the activation operand is written by the convert warps straight into TENSOR MEMORY (tcgen05.st, lane = pixel,
+// one column per k) and the MMAs read it from there, so it never crosses shared memory a second and third time:
+// per 16-channel chunk the shared-memory traffic drops from 116 KB to 76 KB (the mainloop is shared-memory-bandwidth
+// bound).  Needs 2 * npad + 96 <= 512 TMEM columns (npad <= 208); wider outputs keep the A stages in shared memory.
+constexpr int kV3TaHi = 208, kV3TaLo = 464;   // TMEM columns of the A stages: hi in the gap after accumulator 0, lo after 1
+template <bool kTA>
 __global__ void __launch_bounds__(kV3Threads, 1)
 k_inv_w_gemm_tc_v3(TcParams p, int B, int ntiles_per_img, const __grid_constant__ CUtensorMap tmap_x0, int ntmap_chunks) {
   PDES_DYN_SMEM(unsigned char, smem_raw);
@@ -336,8 +342,9 @@ k_inv_w_gemm_tc_v3(TcParams p, int B, int ntiles_per_img, const __grid_constant_
   const uint32_t a_stage = 2 * a_blk, b_stage = 2 * b_blk;
   const int slot_f = kTcBK * (npad > kTcM ? npad : kTcM);         // floats per raw slot
   unsigned char* sA = base;
-  unsigned char* sB = sA + kV3ASt * a_stage;
+  unsigned char* sB = sA + (kTA ? 0 : kV3ASt * a_stage);
   float* raw = reinterpret_cast<float*>(sB + kV3BSt * b_stage);
+  float* tsp = raw + (size_t)kV3Raw * slot_f;                     // [nsp_max*16][128]: fp32 A operand of the spectral chunks
   __shared__ __align__(8) V3Bars bars;
   __shared__ uint32_t tmem_slot;
 
@@ -377,12 +384,30 @@ k_inv_w_gemm_tc_v3(TcParams p, int B, int ntiles_per_img, const __grid_constant_
     const uint32_t row_off = (uint32_t)(tid >> 3) * 128 + (uint32_t)(tid & 7) * 16;
     const uint32_t lbo_b = (uint32_t)(npad / 8) * 128;
     uint32_t g = 0;                                              // global chunk counter
+    // Spectral A operand: A[m][k] = T[j][w(m)] if pixel m sits in row h0 + k/J of the tile (block diagonal over the
+    // tile's rows).  It depends on the tile only through p0 % W, so when every tile starts at column 0
+    // (128 % W == 0, e.g. the shipped W = 64) it is built ONCE per CTA; otherwise it is rebuilt per tile.
+    const bool uniform_geom = (kTcM % W == 0);
+    auto build_tsp = [&](int p0, int h0, int kspec, int nsp) {
+      const int pp = p0 + tid;
+      const bool pv = pp < HW;
+      const int hh = pv ? pp / W : 0, ww = pv ? pp % W : 0;
+      for (int k = 0; k < nsp * kTcBK; ++k) {
+        const int rr = k / J, j = k - rr * J;
+        tsp[k * kTcM + tid] = (pv && k < kspec && hh - h0 == rr) ? __ldg(p.T + (size_t)j * W + ww) : 0.0f;
+      }
+    };
+    if (p.Z != nullptr && uniform_geom && (int)blockIdx.x < ntiles) {
+      int b, p0, h0, kspec, nsp;
+      tile_geom(blockIdx.x, b, p0, h0, kspec, nsp);
+      build_tsp(p0, h0, kspec, nsp);                              // each thread only ever reads its own column
+    }
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
       int b, p0, h0, kspec, nsp;
       tile_geom(t, b, p0, h0, kspec, nsp);
       const int pp = p0 + tid;
       const bool pvalid = pp < HW;
-      const int hh = pvalid ? pp / W : 0, ww = pvalid ? pp % W : 0;
+      if (p.Z != nullptr && !uniform_geom) build_tsp(p0, h0, kspec, nsp);
       for (int c = 0; c < nsp + nx; ++c, ++g) {
         const uint32_t s = g % kV3ASt, r = g % kV3Raw, q = g % kV3BSt;
         if (tid == 0) TRACE(0 * 512 + g * 4 + 0);
@@ -390,6 +415,7 @@ k_inv_w_gemm_tc_v3(TcParams p, int B, int ntiles_per_img, const __grid_constant_
         if (tid == 0) TRACE(0 * 512 + g * 4 + 1);
         unsigned char* st = sA + s * a_stage;
         float v[kTcBK];
+        if (kTA) ptx::tc_fence_after();
         if (c >= nsp) {
           const int cx = c - nsp;
           ptx::mbar_wait(&bars.raw_full[r], (g / kV3Raw) & 1);
@@ -401,11 +427,7 @@ k_inv_w_gemm_tc_v3(TcParams p, int B, int ntiles_per_img, const __grid_constant_
         } else {
           // spectral chunk: A = T[j][w] on this pixel's row, B = Z rows (staged in the raw slot) -> canonical
 #pragma unroll
-          for (int kk = 0; kk < kTcBK; ++kk) {
-            const int k = c * kTcBK + kk;
-            const int rr = k / J, j = k - rr * J;
-            v[kk] = (pvalid && k < kspec && hh - h0 == rr) ? __ldg(p.T + (size_t)j * W + ww) : 0.0f;
-          }
+          for (int kk = 0; kk < kTcBK; ++kk) v[kk] = tsp[(c * kTcBK + kk) * kTcM + tid];
           if (g >= kV3BSt) ptx::mbar_wait(&bars.b_empty[q], ((g / kV3BSt) - 1) & 1);
           ptx::mbar_wait(&bars.raw_full[r], (g / kV3Raw) & 1);
           const float* rw = raw + (size_t)r * slot_f;                     // Z rows: dense [16][N]
@@ -432,18 +454,34 @@ k_inv_w_gemm_tc_v3(TcParams p, int B, int ntiles_per_img, const __grid_constant_
           }
           ptx::mbar_arrive(&bars.raw_empty[r]);
         }
+        if constexpr (kTA) {
+          uint32_t uh[kTcBK], ul[kTcBK];
 #pragma unroll
-        for (int qd = 0; qd < kTcBK / 4; ++qd) {
-          float4 hi, lo;
-          hi.x = tf32_hi(v[4 * qd + 0]); lo.x = v[4 * qd + 0] - hi.x;
-          hi.y = tf32_hi(v[4 * qd + 1]); lo.y = v[4 * qd + 1] - hi.y;
-          hi.z = tf32_hi(v[4 * qd + 2]); lo.z = v[4 * qd + 2] - hi.z;
-          hi.w = tf32_hi(v[4 * qd + 3]); lo.w = v[4 * qd + 3] - hi.w;
-          const uint32_t off = (uint32_t)qd * (kTcM / 8) * 128 + row_off;
-          *reinterpret_cast<float4*>(st + off) = hi;
-          *reinterpret_cast<float4*>(st + a_blk + off) = lo;
+          for (int kk = 0; kk < kTcBK; ++kk) {
+            const float h = tf32_hi(v[kk]);
+            uh[kk] = __float_as_uint(h);
+            ul[kk] = __float_as_uint(v[kk] - h);
+          }
+          const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16) + s * kTcBK;
+          ptx::tmem_st16(trow + kV3TaHi, uh);
+          ptx::tmem_st16(trow + kV3TaLo, ul);
+          ptx::tmem_st_wait();
+          ptx::tc_fence_before();
+          if (c < nsp) ptx::fence_proxy_async();                     // the spectral B block went through st.shared
+        } else {
+#pragma unroll
+          for (int qd = 0; qd < kTcBK / 4; ++qd) {
+            float4 hi, lo;
+            hi.x = tf32_hi(v[4 * qd + 0]); lo.x = v[4 * qd + 0] - hi.x;
+            hi.y = tf32_hi(v[4 * qd + 1]); lo.y = v[4 * qd + 1] - hi.y;
+            hi.z = tf32_hi(v[4 * qd + 2]); lo.z = v[4 * qd + 2] - hi.z;
+            hi.w = tf32_hi(v[4 * qd + 3]); lo.w = v[4 * qd + 3] - hi.w;
+            const uint32_t off = (uint32_t)qd * (kTcM / 8) * 128 + row_off;
+            *reinterpret_cast<float4*>(st + off) = hi;
+            *reinterpret_cast<float4*>(st + a_blk + off) = lo;
+          }
+          ptx::fence_proxy_async();
         }
-        ptx::fence_proxy_async();
         ptx::mbar_arrive(&bars.a_full[s]);
         if (tid == 0) TRACE(0 * 512 + g * 4 + 3);
       }
@@ -481,7 +519,16 @@ k_inv_w_gemm_tc_v3(TcParams p, int B, int ntiles_per_img, const __grid_constant_
 #pragma unroll
           for (int ks = 0; ks < kTcBK / 8; ++ks) {
             const uint64_t ka = da + (uint64_t)((ks * 2 * lbo_a) >> 4), kb = db + (uint64_t)((ks * 2 * lbo_b) >> 4);
-            if (p.single_pass) {
+            if constexpr (kTA) {
+              const uint32_t ta = tmem_base + s * kTcBK + ks * 8;
+              if (p.single_pass) {
+                ptx::mma_tf32_ta(dcol, ta + kV3TaHi, b_hi0 + kb, idesc, (c | ks) != 0 ? 1u : 0u);
+              } else {
+                ptx::mma_tf32_ta(dcol, ta + kV3TaLo, b_hi0 + kb, idesc, (c | ks) != 0 ? 1u : 0u);
+                ptx::mma_tf32_ta(dcol, ta + kV3TaHi, b_lo0 + kb, idesc, 1u);
+                ptx::mma_tf32_ta(dcol, ta + kV3TaHi, b_hi0 + kb, idesc, 1u);
+              }
+            } else if (p.single_pass) {
               ptx::mma_tf32(dcol, a_hi0 + ka, b_hi0 + kb, idesc, (c | ks) != 0 ? 1u : 0u);
             } else {
               ptx::mma_tf32(dcol, a_lo0 + ka, b_hi0 + kb, idesc, (c | ks) != 0 ? 1u : 0u);
@@ -1319,7 +1366,12 @@ int pdes_inv_w_gemm_tc(const float* Z, const float* wpack, const float* x0, int 
   }
   p.out = out; p.pre = pre; p.N = N; p.npad = tc_npad(N); p.K = C0 + C1; p.H = H; p.W = W; p.m2 = m2; p.act = act;
   p.single_pass = (g_tc_mode == 3) ? 1 : 0;
-  if (g_tc_mode >= 2 && (Z == nullptr || N % 4 == 0)) {
+  const int v3_rows = (kTcM + W - 1) / W + 1;
+  const bool v3_ta = tc_npad(N) <= kV3TaHi;          // A operand through tensor memory (no shared-memory A stages)
+  const bool v3_fits = (size_t)(v3_ta ? 0 : kV3ASt) * 2 * kTcM * kTcBK * 4 + (size_t)kV3BSt * 2 * tc_npad(N) * kTcBK * 4 +
+                           (size_t)kV3Raw * kTcBK * (tc_npad(N) > kTcM ? tc_npad(N) : kTcM) * 4 +
+                           (size_t)(Z != nullptr ? tc_nchunks(v3_rows * 2 * m2) : 0) * kTcBK * kTcM * 4 + 2048 <= 227 * 1024;
+  if (g_tc_mode >= 2 && (Z == nullptr || N % 4 == 0) && v3_fits) {
     if (g_num_sms == 0) {
       int dev = 0;
       cudaGetDevice(&dev);
@@ -1327,8 +1379,10 @@ int pdes_inv_w_gemm_tc(const float* Z, const float* wpack, const float* x0, int 
       if (g_num_sms <= 0) g_num_sms = 148;
     }
     const int rawld = p.npad > kTcM ? p.npad : kTcM;
-    const size_t smem3 = (size_t)kV3ASt * 2 * kTcM * kTcBK * 4 + (size_t)kV3BSt * 2 * p.npad * kTcBK * 4 +
-                         (size_t)kV3Raw * kTcBK * rawld * 4 + 1024;
+    const int rows_max = (kTcM + W - 1) / W + 1;
+    const int nsp_max = (Z != nullptr) ? tc_nchunks(rows_max * 2 * m2) : 0;
+    const size_t smem3 = (size_t)(v3_ta ? 0 : kV3ASt) * 2 * kTcM * kTcBK * 4 + (size_t)kV3BSt * 2 * p.npad * kTcBK * 4 +
+                         (size_t)kV3Raw * kTcBK * rawld * 4 + (size_t)nsp_max * kTcBK * kTcM * 4 + 1024;
     const int tiles_per_img = ceil_div(H * W, kTcM);
     const int ntiles = B * tiles_per_img;
     // 2-D tensor map over x0 viewed as [B*C0 rows][HW pixels]; used for the chunks that lie entirely inside x0 when
@@ -1346,7 +1400,7 @@ int pdes_inv_w_gemm_tc(const float* Z, const float* wpack, const float* x0, int 
                                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r == CUDA_SUCCESS) ntmap_chunks = C0 / kTcBK;
     }
-    auto k3 = k_inv_w_gemm_tc_v3;
+    auto k3 = v3_ta ? k_inv_w_gemm_tc_v3<true> : k_inv_w_gemm_tc_v3<false>;
     PDES_SET_SMEM(k3, smem3);
     PDES_LAUNCH(k3, dim3((unsigned)(ntiles < g_num_sms ? ntiles : g_num_sms)), dim3(kV3Threads), smem3, stream, p, B,
                 tiles_per_img, tmap, ntmap_chunks);

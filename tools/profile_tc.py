@@ -5,6 +5,8 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from neural_pde_surrogates_b200 import _native
 lib = _native.library()
+if os.environ.get("PDES_MODE"):
+    lib.pdes_set_tensor_core_mode(int(os.environ["PDES_MODE"]))
 dev = torch.device("cuda:0")
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 16
 variant = sys.argv[2] if len(sys.argv) > 2 else "full"
