@@ -111,6 +111,23 @@ size_t pdes_wgrad_tc_workspace_floats(int M, int K);
 int pdes_wgrad_tc(const float* g, const float* x0, int C0, const float* x1, int C1, float* dW, float* dbias,
                   float* ws, int B, int M, int HW, void* stream);
 
+/* ---- U-Net branch: 1x1 convolutions on the K3b / wgrad tensor-core kernels ---------------
+ * Replaces forward and backward of the nn.Conv2d(k=1) layers of the reference's ResidualBlock shortcut
+ * (proc_unet_modern.py:219-222) -- cuDNN runs them as SIMT sgemm at ~27 TFLOP/s.
+ *   pdes_conv1x1_tc:      out[b,n,p] = act(sum_k Wt[k][n] * x[b,k,p] + bias[n] + res[b,n,p]); x [B][Cin][HW]
+ *                         contiguous, out/res with batch stride out_bstride floats (>= N*HW, so a call can write a
+ *                         channel sub-range of a wider tensor: the input gradient of a 385-channel conv is two
+ *                         calls with N <= 256 each).  wpack = pdes_gemm_tc_pack(Wt, lda, Cin, N).
+ *   pdes_wgrad_tc_range:  dW[o*ldw + i] = sum_{b,p} g[b,o,p] * x[b, c_off + i, p] for i < Cn <= 255 of a tensor with
+ *                         x_ld channels, dbias[o] = sum g (optional); workspace as pdes_wgrad_tc.
+ * Need H*W % 4 == 0 (forward / dX) and H*W % 16 == 0 (weight gradient), 16-byte aligned pointers, tensor-core
+ * mode >= 2; otherwise PDES_ERR_UNSUPPORTED and the caller keeps cuDNN. */
+int pdes_conv1x1_tc_ok(int B, int Cin, int N, int HW, const float* x);
+int pdes_conv1x1_tc(const float* x, int Cin, const float* wpack, const float* bias, const float* res, float* out,
+                    size_t out_bstride, int B, int N, int HW, int act, void* stream);
+int pdes_wgrad_tc_range(const float* g, const float* x, int x_ld, int c_off, int Cn, float* dW, int ldw, float* dbias,
+                        float* ws, int B, int M, int HW, void* stream);
+
 /* ---- U-Net branch: 3x3 valid convolution forward on tcgen05 (3xTF32 implicit GEMM) ------
  * Replaces the forward of the nn.Conv2d(k=3, padding=0) layers of the reference's ResidualBlock
  * (proc_unet_modern.py:217-218, the "circular without padding" valid convs).  Needs W % 4 == 0, H >= 10, W >= 20,

@@ -24,6 +24,24 @@ int check_launch(const char* what) {
   return PDES_OK;
 }
 
+void* tensor_map_encoder() {
+#ifdef PDES_CPU_EMU
+  return nullptr;
+#else
+  static void* fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = sym;
+  }
+  return fn;
+#endif
+}
+
 }  // namespace pdes
 
 extern "C" {

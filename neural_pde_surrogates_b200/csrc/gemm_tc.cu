@@ -76,6 +76,7 @@ struct TcParams {
   float* pre;
   int N, npad, K, H, W, m2, act;
   int single_pass;      // 1 = plain TF32 (hi*hi only): the separately reported reduced-precision mode
+  size_t out_bs;        // batch stride (floats) of out / res / pre: N*H*W, or larger when writing a channel sub-range
 };
 
 constexpr int kTcRaw = 3;          // depth of the raw activation ring fed by bulk async copies
@@ -617,7 +618,7 @@ k_inv_w_gemm_tc_v3(TcParams p, int B, int ntiles_per_img, const __grid_constant_
       tile_geom(t, b, p0, h0, kspec, nsp);
       const int pp = p0 + quad * 32 + lane;
       const bool pvalid = pp < HW;
-      const size_t obase = (size_t)b * N * HW + pp;
+      const size_t obase = (size_t)b * p.out_bs + pp;
       const uint32_t a = it & 1;
       const bool has_res = p.res != nullptr && pvalid;
       const bool has_pre = p.pre != nullptr, do_gelu = p.act == PDES_ACT_GELU;
@@ -718,6 +719,7 @@ struct WgtParams {
   const float* x1; int C1;
   float* part;
   int B, M, C0, K, HW, npadN, mrows, total_chunks, per_cta;
+  int x0_ld, x0_off;    // x0 is the channel range [x0_off, x0_off + C0) of a tensor with x0_ld channels per sample
 };
 
 __global__ void __launch_bounds__(kWgtThreads, 1)
@@ -857,7 +859,7 @@ k_wgrad_tc(WgtParams p, const __grid_constant__ CUtensorMap tmap_g, const __grid
       float* dst = raw + (size_t)r * raw_f;
       ptx::mbar_arrive_expect_tx(&raw_full[r], (uint32_t)(p.M + p.K) * kTcBK * 4);
       ptx::tma_load_2d(dst, &tmap_g, px, b * p.M, &raw_full[r]);
-      ptx::tma_load_2d(dst + off_x0, &tmap_x0, px, b * p.C0, &raw_full[r]);
+      ptx::tma_load_2d(dst + off_x0, &tmap_x0, px, b * p.x0_ld + p.x0_off, &raw_full[r]);
       for (int k = 0; k < p.C1; ++k)
         ptx::bulk_g2s(dst + off_x0 + (p.C0 + k) * kTcBK, p.x1 + ((size_t)b * p.C1 + k) * p.HW + px, kTcBK * 4, &raw_full[r]);
     }
@@ -870,7 +872,7 @@ k_wgrad_tc(WgtParams p, const __grid_constant__ CUtensorMap tmap_g, const __grid
 }
 
 __global__ void __launch_bounds__(256)
-k_wgrad_reduce_ld(const float* __restrict__ part, int nslab, int M, int K, int ld, float* __restrict__ dW,
+k_wgrad_reduce_ld(const float* __restrict__ part, int nslab, int M, int K, int ld, float* __restrict__ dW, int ldw,
                   float* __restrict__ dbias) {
   const int n = M * (K + 1);
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -879,7 +881,7 @@ k_wgrad_reduce_ld(const float* __restrict__ part, int nslab, int M, int K, int l
   float sum = 0.0f;
   for (int s = 0; s < nslab; ++s) sum += __ldg(part + ((size_t)s * M + o) * ld + i);
   if (i < K) {
-    if (dW != nullptr) dW[(size_t)o * K + i] = sum;
+    if (dW != nullptr) dW[(size_t)o * ldw + i] = sum;
   } else if (dbias != nullptr) {
     dbias[o] = sum;
   }
@@ -1190,10 +1192,14 @@ size_t pdes_wgrad_tc_workspace_floats(int M, int K) {
 
 /* dW / dbias of the 1x1 conv on tcgen05 (3xTF32).  Returns PDES_ERR_UNSUPPORTED when the shape does not fit the
  * tensor-core kernel (the caller then uses pdes_wgrad). */
-int pdes_wgrad_tc(const float* g, const float* x0, int C0, const float* x1, int C1, float* dW, float* dbias, float* ws,
-                  int B, int M, int HW, void* stream) {
-  using namespace pdes;
+}  // extern "C"
+
+namespace pdes {
+namespace {
+int wgrad_tc_impl(const float* g, const float* x0, int x0_ld, int x0_off, int C0, const float* x1, int C1, float* dW, int ldw,
+                  float* dbias, float* ws, int B, int M, int HW, void* stream) {
 #ifdef PDES_CPU_EMU
+  (void)x0_ld; (void)x0_off; (void)ldw;
   (void)g; (void)x0; (void)C0; (void)x1; (void)C1; (void)dW; (void)dbias; (void)ws; (void)B; (void)M; (void)HW; (void)stream;
   set_error("pdes_wgrad_tc: tcgen05 path is not available in the CPU emulation build");
   return PDES_ERR_UNSUPPORTED;
@@ -1212,6 +1218,8 @@ int pdes_wgrad_tc(const float* g, const float* x0, int C0, const float* x1, int 
   }
   WgtParams p;
   p.x1 = x1; p.C1 = C1; p.part = ws; p.B = B; p.M = M; p.C0 = C0; p.K = K; p.HW = HW;
+  p.x0_ld = x0_ld; p.x0_off = x0_off;
+  PDES_REQUIRE(x0_ld >= C0 && x0_off >= 0 && x0_off + C0 <= x0_ld && ldw >= K, PDES_ERR_ARG, "pdes_wgrad_tc: bad channel range / ldw");
   p.npadN = tc_npad(K + 1);
   const int mpad = (M + 7) & ~7;
   p.mrows = mpad > 128 ? mpad : 128;
@@ -1237,7 +1245,7 @@ int pdes_wgrad_tc(const float* g, const float* x0, int C0, const float* x1, int 
     PDES_REQUIRE(r == CUDA_SUCCESS, PDES_ERR_UNSUPPORTED, "pdes_wgrad_tc: cuTensorMapEncodeTiled(g) failed (%d)", (int)r);
   }
   {
-    const cuuint64_t gdim[2] = {(cuuint64_t)HW, (cuuint64_t)B * (cuuint64_t)C0};
+    const cuuint64_t gdim[2] = {(cuuint64_t)HW, (cuuint64_t)B * (cuuint64_t)x0_ld};
     const cuuint64_t gstr[1] = {(cuuint64_t)HW * 4};
     const cuuint32_t box[2] = {(cuuint32_t)kTcBK, (cuuint32_t)C0};
     const cuuint32_t estr[2] = {1, 1};
@@ -1252,9 +1260,26 @@ int pdes_wgrad_tc(const float* g, const float* x0, int C0, const float* x1, int 
   if (int e = check_launch("pdes_wgrad_tc")) return e;
   auto rfn = k_wgrad_reduce_ld;
   const int n = M * (K + 1);
-  PDES_LAUNCH(rfn, dim3((unsigned)ceil_div(n, 256)), dim3(256), 0, stream, ws, G, M, K, p.npadN, dW, dbias);
+  PDES_LAUNCH(rfn, dim3((unsigned)ceil_div(n, 256)), dim3(256), 0, stream, ws, G, M, K, p.npadN, dW, ldw, dbias);
   return check_launch("pdes_wgrad_tc_reduce");
 #endif
+}
+}  // namespace
+}  // namespace pdes
+
+extern "C" {
+
+int pdes_wgrad_tc(const float* g, const float* x0, int C0, const float* x1, int C1, float* dW, float* dbias, float* ws,
+                  int B, int M, int HW, void* stream) {
+  return pdes::wgrad_tc_impl(g, x0, C0, 0, C0, x1, C1, dW, C0 + C1, dbias, ws, B, M, HW, stream);
+}
+
+/* Weight / bias gradient of a 1x1 conv for the channel range [c_off, c_off + Cn) of x [B][x_ld][HW]:
+ *   dW[o * ldw + i] = sum_{b,p} g[b,o,p] * x[b, c_off + i, p]  (i < Cn <= 255),  dbias[o] = sum g  (optional).
+ * Same tcgen05 kernel and workspace as pdes_wgrad_tc; wide inputs are covered by several calls. */
+int pdes_wgrad_tc_range(const float* g, const float* x, int x_ld, int c_off, int Cn, float* dW, int ldw, float* dbias,
+                        float* ws, int B, int M, int HW, void* stream) {
+  return pdes::wgrad_tc_impl(g, x, x_ld, c_off, Cn, nullptr, 0, dW, ldw, dbias, ws, B, M, HW, stream);
 }
 
 size_t pdes_conv3x3_tc_pack_floats(int Cin, int N) {
@@ -1336,11 +1361,15 @@ int pdes_gemm_tc_pack(const float* Wt, int lda, int K, int N, float* packed, voi
   return check_launch("pdes_gemm_tc_pack");
 }
 
-int pdes_inv_w_gemm_tc(const float* Z, const float* wpack, const float* x0, int C0, const float* x1, int C1,
+}  // extern "C"
+
+namespace pdes {
+namespace {
+int inv_w_gemm_tc_impl(const float* Z, const float* wpack, const float* x0, int C0, const float* x1, int C1,
                        const float* bias, const float* res, const float* tables, int backward_scale, float* out,
-                       float* pre, int B, int N, int H, int W, int m1, int m2, int act, void* stream) {
-  using namespace pdes;
+                       float* pre, size_t out_bs, int B, int N, int H, int W, int m1, int m2, int act, void* stream) {
 #ifdef PDES_CPU_EMU
+  (void)out_bs;
   (void)Z; (void)wpack; (void)x0; (void)C0; (void)x1; (void)C1; (void)bias; (void)res; (void)tables;
   (void)backward_scale; (void)out; (void)pre; (void)B; (void)N; (void)H; (void)W; (void)m1; (void)m2; (void)act;
   (void)stream;
@@ -1366,6 +1395,8 @@ int pdes_inv_w_gemm_tc(const float* Z, const float* wpack, const float* x0, int 
   }
   p.out = out; p.pre = pre; p.N = N; p.npad = tc_npad(N); p.K = C0 + C1; p.H = H; p.W = W; p.m2 = m2; p.act = act;
   p.single_pass = (g_tc_mode == 3) ? 1 : 0;
+  p.out_bs = out_bs;
+  PDES_REQUIRE(out_bs >= (size_t)N * H * W, PDES_ERR_ARG, "pdes_inv_w_gemm_tc: output batch stride smaller than N*H*W");
   const int v3_rows = (kTcM + W - 1) / W + 1;
   const bool v3_ta = tc_npad(N) <= kV3TaHi;          // A operand through tensor memory (no shared-memory A stages)
   const bool v3_fits = (size_t)(v3_ta ? 0 : kV3ASt) * 2 * kTcM * kTcBK * 4 + (size_t)kV3BSt * 2 * tc_npad(N) * kTcBK * 4 +
@@ -1390,7 +1421,8 @@ int pdes_inv_w_gemm_tc(const float* Z, const float* wpack, const float* x0, int 
     alignas(64) CUtensorMap tmap;
     memset(&tmap, 0, sizeof(tmap));
     int ntmap_chunks = 0;
-    if ((H * W) % kTcM == 0 && g_encode_tiled() != nullptr) {
+    // (a partial last tile of an image is fine: the box columns beyond H*W are out of bounds and arrive as zeros)
+    if ((H * W) % 4 == 0 && g_encode_tiled() != nullptr) {
       const cuuint64_t gdim[2] = {(cuuint64_t)(H * W), (cuuint64_t)B * (cuuint64_t)C0};
       const cuuint64_t gstr[1] = {(cuuint64_t)(H * W) * 4};
       const cuuint32_t box[2] = {(cuuint32_t)kTcM, (cuuint32_t)kTcBK};
@@ -1406,6 +1438,7 @@ int pdes_inv_w_gemm_tc(const float* Z, const float* wpack, const float* x0, int 
                 tiles_per_img, tmap, ntmap_chunks);
     return check_launch("pdes_inv_w_gemm_tc(v3)");
   }
+  PDES_REQUIRE(out_bs == (size_t)N * H * W, PDES_ERR_UNSUPPORTED, "pdes_inv_w_gemm_tc: strided output needs tensor-core mode >= 2");
   const size_t stage = (size_t)2 * kTcM * kTcBK * 4 + (size_t)2 * p.npad * kTcBK * 4;
   const size_t smem = 2 * stage + (size_t)kTcRaw * kTcBK * kTcM * 4 + 1024;
   auto kfn = k_inv_w_gemm_tc;
@@ -1413,6 +1446,35 @@ int pdes_inv_w_gemm_tc(const float* Z, const float* wpack, const float* x0, int 
   PDES_LAUNCH(kfn, dim3((unsigned)ceil_div(H * W, kTcM), (unsigned)B), dim3(kTcThreads), smem, stream, p);
   return check_launch("pdes_inv_w_gemm_tc");
 #endif
+}
+}  // namespace
+}  // namespace pdes
+
+extern "C" {
+
+int pdes_inv_w_gemm_tc(const float* Z, const float* wpack, const float* x0, int C0, const float* x1, int C1,
+                       const float* bias, const float* res, const float* tables, int backward_scale, float* out,
+                       float* pre, int B, int N, int H, int W, int m1, int m2, int act, void* stream) {
+  return pdes::inv_w_gemm_tc_impl(Z, wpack, x0, C0, x1, C1, bias, res, tables, backward_scale, out, pre,
+                                  (size_t)N * H * W, B, N, H, W, m1, m2, act, stream);
+}
+
+int pdes_conv1x1_tc_ok(int B, int Cin, int N, int HW, const float* x) {
+  if (B <= 0 || B > 65535 || Cin <= 0 || HW <= 0 || pdes_get_tensor_core_mode() < 2) return 0;
+  return pdes_inv_w_gemm_tc_ok(N, Cin, 1, HW, 0, x, nullptr);
+}
+
+/* 1x1 convolution (U-Net shortcut / projection convs) on the K3b tensor-core pipeline:
+ *   out[b, n, p] = act(sum_k Wt[k][n] * x[b, k, p] + bias[n] + res[b, n, p]),   x [B][Cin][HW] contiguous,
+ * out / res with batch stride `out_bstride` floats (>= N*HW; lets the caller write a channel sub-range of a wider
+ * tensor, e.g. the two halves of a 385-channel input gradient).  wpack from pdes_gemm_tc_pack(Wt, lda, Cin, N). */
+int pdes_conv1x1_tc(const float* x, int Cin, const float* wpack, const float* bias, const float* res, float* out,
+                    size_t out_bstride, int B, int N, int HW, int act, void* stream) {
+  using namespace pdes;
+  PDES_REQUIRE(HW > 0 && pdes_conv1x1_tc_ok(B, Cin, N, HW, x), PDES_ERR_UNSUPPORTED,
+               "pdes_conv1x1_tc: shape/alignment/mode not supported (Cin=%d N=%d HW=%d)", Cin, N, HW);
+  return inv_w_gemm_tc_impl(nullptr, wpack, x, Cin, nullptr, 0, bias, res, nullptr, 0, out, nullptr, out_bstride, B, N, 1, HW,
+                            0, 0, act, stream);
 }
 
 }  // extern "C"

@@ -35,6 +35,14 @@ int check_launch(const char* what);
     }                                         \
   } while (0)
 
+// driver entry point cuTensorMapEncodeTiled fetched through the runtime (no libcuda link); nullptr if unavailable
+void* tensor_map_encoder();
+// TMA-fed K2 (spectral_mix_tma.cu): reduction splits it wants (0 = unsupported shape) and the launcher
+// (PDES_ERR_UNSUPPORTED = caller falls back to the generic kernels)
+int mix_tma_splits(int B, int Cred, int Cn, int m1, int m2);
+int mix_tma_launch(bool conj, const float* Xin, const float* w1, const float* w2, float* P, int nsplit, int B, int Cred,
+                   int Cn, int Cw_in, int Cw_out, int m1, int m2, int H, void* stream);
+
 // ---- twiddle table blob layout (floats) ---------------------------------------------------------------
 // twh    [H][2]        (cos, sin)(2 pi j / H)
 // twa    [W][NC4]      K1 stage A: col 2l -> cos(2 pi l w / W), col 2l+1 -> -sin(2 pi l w / W), zero padded

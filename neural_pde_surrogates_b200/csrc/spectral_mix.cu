@@ -336,6 +336,7 @@ extern "C" {
 int pdes_mix_suggest_splits(int B, int Cred, int Cout, int m1, int m2) {
   using namespace pdes;
   if (B <= 0 || Cred <= 0 || Cout <= 0 || m1 <= 0 || m2 <= 0) return 1;
+  if (const int ns = mix_tma_splits(B, Cred, Cout, m1, m2)) return ns;
   const int M2 = 2 * m1 * m2;
   const MixGeom g = mix_geom(M2);
   const long blocks = (long)ceil_div(M2, g.bx) * ceil_div(Cout, kTC * g.by) * ceil_div(B, pick_bt(B));
@@ -353,6 +354,7 @@ int pdes_mix_fwd(const float* X, const float* w1, const float* w2, float* P, int
   if (int e = check_mix_args("pdes_mix_fwd", X, w1, w2, P, B, Cin, Cout, H, m1, m2)) return e;
   PDES_REQUIRE(nsplit >= 1 && nsplit <= Cin, PDES_ERR_ARG, "pdes_mix_fwd: bad nsplit %d", nsplit);
   const int MM = m1 * m2;
+  if (mix_tma_launch(false, X, w1, w2, P, nsplit, B, Cin, Cout, Cin, Cout, m1, m2, H, stream) == PDES_OK) return PDES_OK;
   return launch_mix_stream<false>(X, w1, w2, P, nsplit, B, Cin, Cout, MM, m1, m2, H, (long)Cout * MM, (long)MM, stream,
                                   "pdes_mix_fwd");
 }
@@ -364,6 +366,7 @@ int pdes_mix_dx(const float* GO, const float* w1, const float* w2, float* P, int
   PDES_REQUIRE(Cgrad > 0 && Cgrad <= Cin, PDES_ERR_ARG, "pdes_mix_dx: Cgrad %d not in (0,%d]", Cgrad, Cin);
   PDES_REQUIRE(nsplit >= 1 && nsplit <= Cout, PDES_ERR_ARG, "pdes_mix_dx: bad nsplit %d", nsplit);
   const int MM = m1 * m2;
+  if (mix_tma_launch(true, GO, w1, w2, P, nsplit, B, Cout, Cgrad, Cin, Cout, m1, m2, H, stream) == PDES_OK) return PDES_OK;
   const size_t tile = (size_t)ceil_div(Cout, nsplit) * pick_bt(B) * 32 * sizeof(float2);
   if (tile > (size_t)kMaxDynSmem)      // X slice of one split does not fit in shared memory: streaming variant
     return launch_mix_stream<true>(GO, w1, w2, P, nsplit, B, Cout, Cgrad, MM, m1, m2, H, (long)MM, (long)Cout * MM, stream,

@@ -300,6 +300,39 @@ class Conv3x3ValidFunction(torch.autograd.Function):
         return gx, gw, gb
 
 
+class ConvValidDgradAsForwardFunction(torch.autograd.Function):
+    """Stride-1 valid convolution on cuDNN whose input gradient is computed as a FORWARD convolution of the zero-padded
+    output gradient with the flipped, transposed filter.  Same arithmetic as cuDNN's dgrad (fp32, TF32 off), but it lands
+    on cuDNN's forward engines (Winograd, ~150 TFLOP/s fp32-equivalent at the U-Net shapes on B200) instead of its dgrad
+    engines (~50 TFLOP/s): measured 2.7 ms -> 0.9 ms for the 385->192 conv at 100x68, batch 16 (tools/time_conv_bwd.py).
+    Weight and bias gradients stay on cuDNN's wgrad (~120 TFLOP/s)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return torch.nn.functional.conv2d(x, weight, bias)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w = ctx.saved_tensors
+        g = g.contiguous()
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            kh, kw = w.shape[-2:]
+            wt = w.detach().flip(2, 3).transpose(0, 1).contiguous()
+            gx = torch.nn.functional.conv2d(g, wt, None, padding=(kh - 1, kw - 1))
+        need_b = ctx.has_bias and ctx.needs_input_grad[2]
+        if ctx.needs_input_grad[1] or need_b:
+            _, gw, gb = torch.ops.aten.convolution_backward(g, x, w, [w.shape[0]] if ctx.has_bias else None, [1, 1], [0, 0], [1, 1],
+                                                            False, [0, 0], 1, [False, True, bool(need_b)])
+        return gx, gw, gb
+
+
+# cuDNN's fp32 dgrad engines are ~3x slower than its forward engines at the U-Net shapes: route dx through a forward conv
+enable_dgrad_as_forward = True
+
+
 def conv3x3_valid(x, conv):
     """conv(x) for the U-Net's 3x3 valid convolutions: tcgen05 implicit GEMM (3xTF32) when the shape allows, else cuDNN."""
     if (x.is_cuda and x.dtype == torch.float32 and isinstance(conv, torch.nn.Conv2d) and tuple(conv.kernel_size) == (3, 3)
@@ -311,6 +344,11 @@ def conv3x3_valid(x, conv):
         xc = x if x.is_contiguous() else x.contiguous()
         if lib.pdes_get_tensor_core_mode() >= 2 and lib.pdes_conv3x3_tc_ok(B, Cin, conv.out_channels, H, W, xc.data_ptr()):
             return Conv3x3ValidFunction.apply(xc, conv.weight, conv.bias)
+    if (enable_dgrad_as_forward and x.is_cuda and x.dim() == 4 and isinstance(conv, torch.nn.Conv2d)
+            and tuple(conv.stride) == (1, 1) and tuple(conv.dilation) == (1, 1) and conv.groups == 1
+            and not isinstance(conv.padding, str) and tuple(conv.padding) == (0, 0) and torch.is_grad_enabled()
+            and (x.requires_grad or conv.weight.requires_grad)):
+        return ConvValidDgradAsForwardFunction.apply(x, conv.weight, conv.bias)
     return conv(x)
 
 
@@ -318,3 +356,89 @@ def conv3x3_valid(x, conv):
 # accurate (the fp32 accumulation of tcgen05 truncates, so 3xTF32 reaches 1.4e-5 .. 2.6e-5 rel. L2 at K = Cin*9 > 1700,
 # above the 1e-5 bar); kept as an opt-in experiment for the next round (split-K over several TMEM accumulators).
 enable_conv_tc = False
+
+
+# ---- U-Net branch: 1x1 convolutions on the K3b / weight-gradient tensor-core kernels ---------
+enable_conv1x1_tc = True
+_C1_MAX_N = 208          # output channels per launch (tensor-memory A-operand path of the K3b kernel)
+_C1_MAX_WG = 255         # input channels per weight-gradient launch (K + 1 ones column <= 256)
+
+
+def _ranges(total: int, cap: int):
+    parts = -(-total // cap)
+    size = -(-total // parts)
+    return [(o, min(size, total - o)) for o in range(0, total, size)]
+
+
+class Conv1x1Function(torch.autograd.Function):
+    """y = conv2d(x, w[N,Cin,1,1], b) and its three gradients on tcgen05 (3xTF32), replacing cuDNN's SIMT sgemm for the
+    shortcut convs of the reference's ResidualBlock (proc_unet_modern.py:219-222) and the encoder/decoder 1x1 convs."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        lib = _lib()
+        B, Cin, H, W = x.shape
+        N, HW = weight.shape[0], H * W
+        dev = x.device
+        p = lambda t: None if t is None else t.data_ptr()
+        with torch.cuda.device(dev):
+            wt = weight.detach().reshape(N, Cin).t().contiguous()                  # [Cin][N]
+            pack = torch.empty(lib.pdes_gemm_tc_pack_floats(Cin, N), dtype=torch.float32, device=dev)
+            out = torch.empty(B, N, H, W, dtype=torch.float32, device=dev)
+            st = _stream()
+            _native.check(lib, lib.pdes_gemm_tc_pack(p(wt), N, Cin, N, p(pack), st))
+            _native.check(lib, lib.pdes_conv1x1_tc(p(x), Cin, p(pack), p(bias), None, p(out), N * HW, B, N, HW, ACT_NONE, st))
+            _counters["launches"] += 3
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib()
+        x, weight = ctx.saved_tensors
+        B, Cin, H, W = x.shape
+        N, HW = weight.shape[0], H * W
+        dev = x.device
+        g = g.contiguous()
+        p = lambda t: None if t is None else t.data_ptr()
+        gx = gw = gb = None
+        with torch.cuda.device(dev):
+            st = _stream()
+            w2 = weight.detach().reshape(N, Cin)
+            if not w2.is_contiguous():
+                w2 = w2.contiguous()
+            if ctx.needs_input_grad[0]:
+                gx = torch.empty_like(x)
+                pack = torch.empty(lib.pdes_gemm_tc_pack_floats(N, min(Cin, _C1_MAX_N)), dtype=torch.float32, device=dev)
+                for off, n in _ranges(Cin, _C1_MAX_N):            # dx[:, off:off+n] = w[:, off:off+n]^T g
+                    _native.check(lib, lib.pdes_gemm_tc_pack(p(w2) + 4 * off, Cin, N, n, p(pack), st))
+                    _native.check(lib, lib.pdes_conv1x1_tc(p(g), N, p(pack), None, None, p(gx) + 4 * off * HW, Cin * HW, B, n, HW,
+                                                           ACT_NONE, st))
+                    _counters["launches"] += 2
+            if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+                gw = torch.empty(N, Cin, dtype=torch.float32, device=dev)
+                gb = torch.empty(N, dtype=torch.float32, device=dev) if ctx.has_bias else None
+                ws = torch.empty(lib.pdes_wgrad_tc_workspace_floats(N, min(Cin, _C1_MAX_WG)), dtype=torch.float32, device=dev)
+                for k, (off, n) in enumerate(_ranges(Cin, _C1_MAX_WG)):
+                    _native.check(lib, lib.pdes_wgrad_tc_range(p(g), p(x), Cin, off, n, p(gw) + 4 * off, Cin, p(gb) if k == 0 else None,
+                                                               p(ws), B, N, HW, st))
+                    _counters["launches"] += 2
+                gw = gw.view_as(weight)
+        return gx, gw, gb
+
+
+def conv1x1(x, conv):
+    """conv(x) for a kernel_size=1 nn.Conv2d: tcgen05 GEMM kernels when the shape allows, else the module itself (cuDNN)."""
+    if (enable_conv1x1_tc and x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and isinstance(conv, torch.nn.Conv2d)
+            and tuple(conv.kernel_size) == (1, 1) and tuple(conv.stride) == (1, 1) and conv.groups == 1
+            and tuple(conv.dilation) == (1, 1) and not isinstance(conv.padding, str) and tuple(conv.padding) == (0, 0)):
+        lib = _lib()
+        B, Cin, H, W = x.shape
+        N, HW = conv.out_channels, H * W
+        xc = x if x.is_contiguous() else x.contiguous()
+        if (HW % 16 == 0 and 8 <= N <= 256 and Cin >= 8
+                and (conv.bias is None or conv.bias.data_ptr() % 16 == 0)
+                and lib.pdes_conv1x1_tc_ok(B, Cin, N, HW, xc.data_ptr())):
+            return Conv1x1Function.apply(xc, conv.weight, conv.bias)
+    return conv(x)

@@ -18,6 +18,7 @@ from types import SimpleNamespace
 import torch
 from torch import nn
 
+from . import ops
 from .proc_fno import FNO
 from .proc_ufno import UFNO
 from .unet_branch import UNetModern
@@ -50,7 +51,10 @@ class ElementWise(nn.Module):
         parts = [u.flatten(1, 2), torch.movedim(pos, -1, 1)]
         if variables_broadcast is not None:
             parts.append(variables_broadcast)
-        return self.encoder(torch.cat(parts, dim=1))
+        h = torch.cat(parts, dim=1)
+        for layer in self.encoder:                                # 1x1 convs on the tensor-core GEMM kernels
+            h = ops.conv1x1(h, layer) if isinstance(layer, nn.Conv2d) else layer(h)
+        return h
 
 
 class TimeConvDense(nn.Module):
@@ -71,7 +75,7 @@ class TimeConvDense(nn.Module):
                                      nn.Conv1d(num_c * 2, num_c, kb, stride=1))
 
     def forward(self, h, u, **kwargs):
-        z = self.pre_decoder(h)                                   # [b, 3*tw*c, H, W]
+        z = ops.conv1x1(h, self.pre_decoder)                     # [b, 3*tw*c, H, W]
         b, _, H, W = z.shape
         z = z.permute(0, 2, 3, 1).reshape(b * H * W, self.num_c, self.time_window * 3)
         delta = self.decoder(z).view(b, H, W, self.num_c, self.time_window).permute(0, 3, 4, 1, 2)

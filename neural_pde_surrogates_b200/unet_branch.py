@@ -72,7 +72,7 @@ class ResidualBlock(nn.Module):
     def forward(self, x):
         y = ops.conv3x3_valid(ops.group_norm_act(x, self.norm1, self.activation), self.conv1)
         y = ops.conv3x3_valid(ops.group_norm_act(y, self.norm2, self.activation), self.conv2)
-        skip = self.shortcut(x)
+        skip = ops.conv1x1(x, self.shortcut) if isinstance(self.shortcut, nn.Conv2d) else x
         return fit_to(y, skip.shape[-2:]) + skip
 
 
@@ -243,4 +243,6 @@ class UNetModern(nn.Module):
             if c is not None:
                 parts.append(fit_to(c, here))
             h = m(torch.cat(parts, dim=1))
-        return fit_to(self.final(ops.group_norm_act(h, self.norm, self.activation)), target)
+        z = ops.group_norm_act(h, self.norm, self.activation)
+        z = ops.conv1x1(z, self.final) if tuple(self.final.kernel_size) == (1, 1) else self.final(z)
+        return fit_to(z, target)

@@ -195,3 +195,40 @@ def test_conv3x3_valid_tcgen05_vs_torch(shape):
     assert rel_l2(x.grad, xd.grad) < 1e-5
     assert rel_l2(conv.weight.grad, convd.weight.grad) < 1e-5
     assert rel_l2(conv.bias.grad, convd.bias.grad) < 1e-5
+
+
+@pytest.mark.parametrize("shape", [(2, 385, 192, 100, 68), (2, 193, 192, 96, 64), (3, 40, 75, 16, 16), (1, 192, 192, 20, 12),
+                                   (2, 27, 192, 8, 6), (1, 300, 24, 4, 4)])
+@pytest.mark.parametrize("bias", [True, False])
+def test_conv1x1_tcgen05_vs_torch(shape, bias):
+    """U-Net / encoder / decoder 1x1 convs on the K3b + weight-gradient tensor-core kernels (3xTF32): forward and all
+    three gradients vs PyTorch float64.  Covers wide inputs (385 channels = two dX launches and two weight-gradient
+    launches writing channel sub-ranges), partial 128-pixel tiles (H*W % 128 != 0) and few-channel inputs."""
+    from neural_pde_surrogates_b200 import ops
+    B, Cin, N, H, W = shape
+    torch.manual_seed(1)
+    conv = torch.nn.Conv2d(Cin, N, 1, bias=bias).to(DEV)
+    x = torch.randn(B, Cin, H, W, device=DEV, requires_grad=True)
+    y = ops.conv1x1(x, conv)
+    assert y.grad_fn is not None and "Conv1x1" in type(y.grad_fn).__name__, "tensor-core path not taken"
+    g = torch.randn_like(y)
+    y.backward(g)
+    convd = torch.nn.Conv2d(Cin, N, 1, bias=bias).to(DEV).double()
+    convd.load_state_dict({k: v.double() for k, v in conv.state_dict().items()})
+    xd = x.detach().double().requires_grad_()
+    yd = convd(xd)
+    yd.backward(g.double())
+    assert rel_l2(y, yd) < 1e-5
+    assert rel_l2(x.grad, xd.grad) < 1e-5
+    assert rel_l2(conv.weight.grad, convd.weight.grad) < 1e-5
+    if bias:
+        assert rel_l2(conv.bias.grad, convd.bias.grad) < 1e-5
+
+
+def test_conv1x1_falls_back_to_cudnn_when_unsupported():
+    from neural_pde_surrogates_b200 import ops
+    conv = torch.nn.Conv2d(193, 192, 1).to(DEV)
+    x = torch.randn(2, 193, 47, 31, device=DEV, requires_grad=True)          # H*W odd: no 16-byte row stride for TMA
+    y = ops.conv1x1(x, conv)
+    assert "Conv1x1" not in type(y.grad_fn).__name__
+    assert rel_l2(y, conv(x)) == 0.0
