@@ -111,6 +111,19 @@ size_t pdes_wgrad_tc_workspace_floats(int M, int K);
 int pdes_wgrad_tc(const float* g, const float* x0, int C0, const float* x1, int C1, float* dW, float* dbias,
                   float* ws, int B, int M, int HW, void* stream);
 
+/* ---- decoder: fused per-pixel temporal Conv1d stack of TimeConvDense ------------------------
+ * Replaces `self.decoder(z)` of reference dec_grid.py:97-146 (permute + Conv1d(1->2,k=13,s=2) + act + Conv1d(2->1,k=8)
+ * per pixel) for time_window = 25, one field.  z [B][75][HW] (output of the 1x1 pre-decoder, no permute),
+ * out / gy [B][25][HW], w1 [2][1][13], b1 [2], w2 [1][2][8], b2 [1].  Backward writes dz and all weight gradients
+ * (deterministic two-stage reduction); ws needs pdes_timeconv_bwd_workspace_floats() floats. */
+int pdes_timeconv_ok(int time_window, int num_c);
+int pdes_timeconv_forward(const float* z, const float* w1, const float* b1, const float* w2, const float* b2, float* out,
+                          int B, int HW, int time_window, int act, void* stream);
+size_t pdes_timeconv_bwd_workspace_floats(int B, int HW, int time_window);
+int pdes_timeconv_backward(const float* z, const float* gy, const float* w1, const float* b1, const float* w2,
+                           const float* b2, float* dz, float* dw1, float* db1, float* dw2, float* db2, float* ws, int B,
+                           int HW, int time_window, int act, void* stream);
+
 /* ---- U-Net branch: 1x1 convolutions on the K3b / wgrad tensor-core kernels ---------------
  * Replaces forward and backward of the nn.Conv2d(k=1) layers of the reference's ResidualBlock shortcut
  * (proc_unet_modern.py:219-222) -- cuDNN runs them as SIMT sgemm at ~27 TFLOP/s.

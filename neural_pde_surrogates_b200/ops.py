@@ -442,3 +442,64 @@ def conv1x1(x, conv):
                 and lib.pdes_conv1x1_tc_ok(B, Cin, N, HW, xc.data_ptr())):
             return Conv1x1Function.apply(xc, conv.weight, conv.bias)
     return conv(x)
+
+
+# ---- decoder: fused per-pixel temporal Conv1d stack of TimeConvDense -----------------------
+enable_timeconv = True
+
+
+class TimeConvFunction(torch.autograd.Function):
+    """delta[b, 0, t, h, w] = Conv1d(2->1,k=8)(act(Conv1d(1->2,k=13,s=2)(z[b, :, h, w])))  (reference dec_grid.py:97-146),
+    one thread per pixel, no permute copies; the backward recomputes the hidden layer."""
+
+    @staticmethod
+    def forward(ctx, z, w1, b1, w2, b2, act):
+        lib = _lib()
+        B, C3, H, W = z.shape
+        tw = C3 // 3
+        dev = z.device
+        p = lambda t: t.data_ptr()
+        ws_ = [t.detach().contiguous() for t in (w1, b1, w2, b2)]
+        with torch.cuda.device(dev):
+            out = torch.empty(B, 1, tw, H, W, dtype=torch.float32, device=dev)
+            _native.check(lib, lib.pdes_timeconv_forward(p(z), p(ws_[0]), p(ws_[1]), p(ws_[2]), p(ws_[3]), p(out), B, H * W, tw,
+                                                         act, _stream()))
+            _counters["launches"] += 1
+        ctx.save_for_backward(z, *ws_)
+        ctx.act = act
+        return out
+
+    @staticmethod
+    def backward(ctx, gy):
+        lib = _lib()
+        z, w1, b1, w2, b2 = ctx.saved_tensors
+        B, C3, H, W = z.shape
+        tw = C3 // 3
+        dev = z.device
+        gy = gy.contiguous()
+        p = lambda t: t.data_ptr()
+        with torch.cuda.device(dev):
+            dz = torch.empty_like(z)
+            dw1, db1, dw2, db2 = (torch.empty_like(t) for t in (w1, b1, w2, b2))
+            ws = torch.empty(lib.pdes_timeconv_bwd_workspace_floats(B, H * W, tw), dtype=torch.float32, device=dev)
+            _native.check(lib, lib.pdes_timeconv_backward(p(z), p(gy), p(w1), p(b1), p(w2), p(b2), p(dz), p(dw1), p(db1), p(dw2),
+                                                          p(db2), p(ws), B, H * W, tw, ctx.act, _stream()))
+            _counters["launches"] += 2
+        return dz, dw1, db1, dw2, db2, None
+
+
+def timeconv_decoder(z, decoder, num_c: int, time_window: int):
+    """decoder = nn.Sequential(Conv1d, act, Conv1d) applied per pixel along the channel axis of z [B, num_c*3*tw, H, W];
+    returns [B, num_c, tw, H, W].  Fused kernel for the shipped decoder (tw = 25, one field, GELU / identity), else torch."""
+    B, _, H, W = z.shape
+    if enable_timeconv and z.is_cuda and z.dtype == torch.float32 and len(decoder) == 3:
+        c1, a, c2 = decoder[0], decoder[1], decoder[2]
+        code = act_code(a)
+        if (code is not None and isinstance(c1, torch.nn.Conv1d) and isinstance(c2, torch.nn.Conv1d)
+                and c1.bias is not None and c2.bias is not None and tuple(c1.stride) == (2,) and tuple(c2.stride) == (1,)
+                and tuple(c1.padding) == (0,) and tuple(c2.padding) == (0,) and c1.groups == 1 and c2.groups == 1
+                and _lib().pdes_timeconv_ok(time_window, num_c)):
+            zc = z if z.is_contiguous() else z.contiguous()
+            return TimeConvFunction.apply(zc, c1.weight, c1.bias, c2.weight, c2.bias, code)
+    zz = z.permute(0, 2, 3, 1).reshape(B * H * W, num_c, time_window * 3)
+    return decoder(zz).view(B, H, W, num_c, time_window).permute(0, 3, 4, 1, 2)

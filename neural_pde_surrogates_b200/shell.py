@@ -76,9 +76,7 @@ class TimeConvDense(nn.Module):
 
     def forward(self, h, u, **kwargs):
         z = ops.conv1x1(h, self.pre_decoder)                     # [b, 3*tw*c, H, W]
-        b, _, H, W = z.shape
-        z = z.permute(0, 2, 3, 1).reshape(b * H * W, self.num_c, self.time_window * 3)
-        delta = self.decoder(z).view(b, H, W, self.num_c, self.time_window).permute(0, 3, 4, 1, 2)
+        delta = ops.timeconv_decoder(z, self.decoder, self.num_c, self.time_window)   # [b, c, tw, H, W]
         dt = self.pde.dt if self.dec_delta_dt else 1
         steps = torch.cumsum(torch.full((1, 1, self.time_window, 1, 1), dt, device=h.device), dim=2)
         return u[:, :, -1:] + steps * delta

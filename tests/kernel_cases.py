@@ -361,3 +361,47 @@ def check_wgrad_tc(be, shape):
     e3 = so.rel_l2(be.download(db), g.astype(np.float64).sum(axis=(0, 2, 3)))
     assert e2 < TOL and e3 < TOL, f"wgrad_tc {shape}: dW {e2:.3e} dbias {e3:.3e}"
     return e2, e3
+
+
+def check_timeconv(be, B=2, HW=200, act=1, tw=25):
+    """Fused temporal decoder (TimeConvDense Conv1d stack, dec_grid.py:97-146) forward/backward vs float64 numpy."""
+    rng = _rng(33)
+    KA, KB = 13, 8
+    L1 = (3 * tw - KA) // 2 + 1
+    z = rng.standard_normal((B, 3 * tw, HW)).astype(np.float32)
+    gy = rng.standard_normal((B, tw, HW)).astype(np.float32)
+    w1 = (0.3 * rng.standard_normal((2, 1, KA))).astype(np.float32); b1 = (0.1 * rng.standard_normal(2)).astype(np.float32)
+    w2 = (0.3 * rng.standard_normal((1, 2, KB))).astype(np.float32); b2 = (0.1 * rng.standard_normal(1)).astype(np.float32)
+    dz_, dg_, dw1, db1, dw2, db2 = (be.upload(a) for a in (z, gy, w1, b1, w2, b2))
+    out = be.empty((B, tw, HW))
+    be.check(be.lib.pdes_timeconv_forward(be.ptr(dz_), be.ptr(dw1), be.ptr(db1), be.ptr(dw2), be.ptr(db2), be.ptr(out), B, HW, tw,
+                                          act, be.stream))
+    gz = be.empty((B, 3 * tw, HW)); gw1 = be.empty((2, 1, KA)); gb1 = be.empty((2,)); gw2 = be.empty((1, 2, KB)); gb2 = be.empty((1,))
+    ws = be.empty((max(1, be.lib.pdes_timeconv_bwd_workspace_floats(B, HW, tw)),))
+    be.check(be.lib.pdes_timeconv_backward(be.ptr(dz_), be.ptr(dg_), be.ptr(dw1), be.ptr(db1), be.ptr(dw2), be.ptr(db2), be.ptr(gz),
+                                           be.ptr(gw1), be.ptr(gb1), be.ptr(gw2), be.ptr(gb2), be.ptr(ws), B, HW, tw, act, be.stream))
+    # float64 restatement
+    zd, gd = z.astype(np.float64), gy.astype(np.float64)
+    idx = 2 * np.arange(L1)[:, None] + np.arange(KA)[None, :]                        # [L1][KA]
+    zw = zd[:, idx, :]                                                                # [B][L1][KA][HW]
+    h = np.einsum("ok,blkp->bolp", w1[:, 0].astype(np.float64), zw) + b1[None, :, None, None]
+    a = so.gelu(h) if act else h
+    tdx = np.arange(tw)[:, None] + np.arange(KB)[None, :]                             # [tw][KB]
+    aw = a[:, :, tdx, :]                                                              # [B][2][tw][KB][HW]
+    y = np.einsum("ok,botkp->btp", w2[0].astype(np.float64), aw) + b2[0]
+    da = np.zeros_like(a)
+    for k in range(KB):
+        da[:, :, k:k + tw, :] += w2[0][None, :, k, None, None] * gd[:, None, :, :]
+    dh = da * (so.gelu_grad(h) if act else 1.0)
+    dzr = np.zeros_like(zd)
+    for k in range(KA):
+        dzr[:, k:k + 2 * L1:2, :] += np.einsum("o,bolp->blp", w1[:, 0, k].astype(np.float64), dh)
+    dw1r = np.einsum("bolp,blkp->ok", dh, zw)[:, None, :]
+    db1r = dh.sum(axis=(0, 2, 3))
+    dw2r = np.einsum("btp,botkp->ok", gd, aw)[None]
+    db2r = gd.sum()[None]
+    errs = dict(y=so.rel_l2(be.download(out), y), dz=so.rel_l2(be.download(gz), dzr), dw1=so.rel_l2(be.download(gw1), dw1r),
+                db1=so.rel_l2(be.download(gb1), db1r), dw2=so.rel_l2(be.download(gw2), dw2r), db2=so.rel_l2(be.download(gb2), db2r))
+    for k, v in errs.items():
+        assert v < TOL, f"timeconv {k}: {v:.3e}"
+    return errs

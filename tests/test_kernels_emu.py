@@ -74,3 +74,8 @@ def test_groupnorm_act(be):
     kc.check_groupnorm(be, B=3, C=12, HW=35, G=4, act=1)       # scalar path
     kc.check_groupnorm(be, B=2, C=10, HW=64, G=1, act=1)       # GroupNorm(1, C) as in the residual blocks, vector path
     kc.check_groupnorm(be, B=2, C=8, HW=16, G=8, act=0)
+
+
+def test_timeconv_decoder(be):
+    kc.check_timeconv(be, B=2, HW=150, act=1)         # partial last block
+    kc.check_timeconv(be, B=1, HW=128, act=0)

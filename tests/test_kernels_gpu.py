@@ -117,3 +117,9 @@ def test_tc_wgrad(be, shape):
 def test_tc_wgrad_path_is_taken_for_config_shapes(be):
     for shape in FULL_SHAPES + [(2, 20, 1, 24, 8, 24, 3, 4), (1, 40, 0, 200, 16, 32, 5, 7)]:
         assert kc.check_wgrad_tc(be, shape) is not None
+
+
+def test_timeconv_decoder(be):
+    kc.check_timeconv(be, B=2, HW=150, act=1)
+    kc.check_timeconv(be, B=1, HW=128, act=0)
+    kc.check_timeconv(be, B=4, HW=96 * 64, act=1)     # the decoder shape of the twophase config
