@@ -25,6 +25,7 @@
 #ifndef PDES_CPU_EMU
 #include <cuda.h>      // CUtensorMap types only; the encoder is fetched with cudaGetDriverEntryPoint (no libcuda link)
 #include <cstring>
+#include <cstdlib>
 #endif
 
 namespace pdes {
@@ -314,27 +315,49 @@ k_inv_w_gemm_tc(TcParams p) {
 //                          main loop through the second accumulator
 #ifdef PDES_TC_TRACE
 __device__ long long g_trace[4096];
+#if PDES_TC_TRACE == 2       // MMA-issue thread only: 10 stamps per chunk (start, a_full, b_full, 6 MMAs, commits)
+#define TRACE(slot) do { } while (0)
+#define TRACE2(slot) do { if (blockIdx.x == 0 && (slot) < 4096) g_trace[(slot)] = clock64(); } while (0)
+#else
 #define TRACE(slot) do { if (blockIdx.x == 0 && (slot) < 4096) g_trace[(slot)] = clock64(); } while (0)
+#define TRACE2(slot) do { } while (0)
+#endif
 #else
 #define TRACE(slot) do { } while (0)
+#define TRACE2(slot) do { } while (0)
 #endif
 constexpr int kV3Threads = 768;       // 8 service warps + 16 epilogue warps
 constexpr int kV3EpiParts = 4;         // epilogue warps per TMEM lane quadrant
-constexpr int kV3ASt = 3, kV3BSt = 4, kV3Raw = 3;
+constexpr int kV3ASt = 3, kV3BSt = 4, kV3Raw = 3;   // (ring depths of the 3x3-conv kernel below)
+constexpr int kV3MaxSt = 4, kV3MaxRaw = 8;
 
 struct V3Bars {
   unsigned long long a_full[kV3ASt], a_empty[kV3ASt], b_full[kV3BSt], b_empty[kV3BSt], raw_full[kV3Raw],
       raw_empty[kV3Raw], acc_full[2], acc_empty[2];
 };
 
+// One ring of NST operand stages (A and B share the index): full[s] = 128 convert arrivals + 1 arrival (carrying the byte
+// count of the weight copy) of the B-issue thread, empty[s] = ONE tcgen05.commit.  The MMA thread therefore pays one
+// wait and one commit per chunk: its serial overhead between chunks is what the tensor pipe idles on.
+struct V3RingBars {
+  unsigned long long full[kV3MaxSt], empty[kV3MaxSt], raw_full[kV3MaxRaw], raw_empty[kV3MaxRaw], acc_full[2], acc_empty[2];
+};
+
+// Warp roles of the K3b kernel (896 threads): warps 0-7 convert (two groups of 4 that take alternate chunks), 8-23
+// epilogue (4 per TMEM lane quadrant), 24 MMA issue, 25 activation copies, 26 weight copies.
+constexpr int kK3Threads = 896, kK3EpiParts = 4, kK3MmaWarp = 24, kK3RawWarp = 25, kK3WgtWarp = 26;
+
 // kTA: the activation operand is written by the convert warps straight into TENSOR MEMORY (tcgen05.st, lane = pixel,
 // one column per k) and the MMAs read it from there, so it never crosses shared memory a second and third time:
 // per 16-channel chunk the shared-memory traffic drops from 116 KB to 76 KB (the mainloop is shared-memory-bandwidth
-// bound).  Needs 2 * npad + 96 <= 512 TMEM columns (npad <= 208); wider outputs keep the A stages in shared memory.
-constexpr int kV3TaHi = 208, kV3TaLo = 464;   // TMEM columns of the A stages: hi in the gap after accumulator 0, lo after 1
+// bound).  Needs 2 * npad + 2 * 16 * NST <= 512 TMEM columns: NST = 4 stages for npad <= 192, 3 for npad <= 208; wider
+// outputs keep (3) A stages in shared memory.  The hi halves sit in the gap below column 256 (after accumulator 0), the
+// lo halves below column 512 (after accumulator 1).
+constexpr int kV3TaMaxN = 208;
 template <bool kTA>
-__global__ void __launch_bounds__(kV3Threads, 1)
-k_inv_w_gemm_tc_v3(TcParams p, int B, int ntiles_per_img, const __grid_constant__ CUtensorMap tmap_x0, int ntmap_chunks) {
+__global__ void __launch_bounds__(kK3Threads, 1)
+k_inv_w_gemm_tc_v3(TcParams p, int B, int ntiles_per_img, const __grid_constant__ CUtensorMap tmap_x0, int ntmap_chunks,
+                   int NST, int NRAW) {
   PDES_DYN_SMEM(unsigned char, smem_raw);
   unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int npad = p.npad;
@@ -343,25 +366,33 @@ k_inv_w_gemm_tc_v3(TcParams p, int B, int ntiles_per_img, const __grid_constant_
   const uint32_t a_stage = 2 * a_blk, b_stage = 2 * b_blk;
   const int slot_f = kTcBK * (npad > kTcM ? npad : kTcM);         // floats per raw slot
   unsigned char* sA = base;
-  unsigned char* sB = sA + (kTA ? 0 : kV3ASt * a_stage);
-  float* raw = reinterpret_cast<float*>(sB + kV3BSt * b_stage);
-  float* tsp = raw + (size_t)kV3Raw * slot_f;                     // [nsp_max*16][128]: fp32 A operand of the spectral chunks
-  __shared__ __align__(8) V3Bars bars;
+  unsigned char* sB = sA + (kTA ? 0 : NST * a_stage);
+  float* raw = reinterpret_cast<float*>(sB + NST * b_stage);
+  const uint32_t ta_hi = 256u - 16u * NST, ta_lo = 512u - 16u * NST;   // TMEM columns of the A stages (kTA)
+  float* tsp = raw + (size_t)NRAW * slot_f;                     // [nsp_max*16][128]: fp32 A operand of the spectral chunks
+  __shared__ __align__(8) V3RingBars bars;
   __shared__ uint32_t tmem_slot;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int HW = p.H * p.W, W = p.W, J = 2 * p.m2;
   const int nx = tc_nchunks(p.K);
   const int ntiles = B * ntiles_per_img;
+#ifdef PDES_TC_TRACE
+  const int dbg = p.act >> 8;        // ablation mask (trace builds only): 1 no MMA, 2 no weight copy, 4 no raw copy, 8 no convert
+  p.act &= 255;
+#else
+  constexpr int dbg = 0;
+#endif
 
   if (tid == 0) {
-    for (int i = 0; i < kV3ASt; ++i) { ptx::mbar_init(&bars.a_full[i], 128); ptx::mbar_init(&bars.a_empty[i], 1); }
-    for (int i = 0; i < kV3BSt; ++i) { ptx::mbar_init(&bars.b_full[i], 1); ptx::mbar_init(&bars.b_empty[i], 1); }
-    for (int i = 0; i < kV3Raw; ++i) { ptx::mbar_init(&bars.raw_full[i], 1); ptx::mbar_init(&bars.raw_empty[i], 128); }
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&bars.acc_full[i], 1); ptx::mbar_init(&bars.acc_empty[i], 32 * 4 * kV3EpiParts); }
+    // ONE arrival per warp (after __syncwarp), not one per thread: 128 arrivals on one barrier word serialise at a few
+    // cycles each, and two such barriers per chunk were ~800 cycles of the ~1250-cycle chunk period.
+    for (int i = 0; i < NST; ++i) { ptx::mbar_init(&bars.full[i], 4 + 1); ptx::mbar_init(&bars.empty[i], 1); }
+    for (int i = 0; i < NRAW; ++i) { ptx::mbar_init(&bars.raw_full[i], 1); ptx::mbar_init(&bars.raw_empty[i], 4); }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&bars.acc_full[i], 1); ptx::mbar_init(&bars.acc_empty[i], 4 * kK3EpiParts); }
     ptx::fence_mbar_init();
   }
-  if (warp == 4) {
+  if (warp == kK3MmaWarp) {
     ptx::tmem_alloc(&tmem_slot, 512);
     ptx::tmem_relinquish();
   }
@@ -380,11 +411,15 @@ k_inv_w_gemm_tc_v3(TcParams p, int B, int ntiles_per_img, const __grid_constant_
     nsp = tc_nchunks(kspec);
   };
 
-  if (warp < 4) {
-    // ================================================================== convert
+  if (warp < 8) {
+    // ================================================================== convert (group = warp / 4 takes chunks g % 2 == group)
+    const int grp = warp >> 2, cwarp = warp & 3;
+    const int tid = threadIdx.x & 127;                             // pixel / TMEM lane of this thread (shadows the CTA-wide tid)
+    auto cvt_sync = [] { asm volatile("bar.sync 1, 256;" ::: "memory"); };
     const uint32_t row_off = (uint32_t)(tid >> 3) * 128 + (uint32_t)(tid & 7) * 16;
     const uint32_t lbo_b = (uint32_t)(npad / 8) * 128;
-    uint32_t g = 0;                                              // global chunk counter
+    uint32_t g = 0, s = 0, sph = 1;                              // global chunk counter, ring slot and its "empty" parity
+    uint32_t r = 0, rph = 0;                                     // raw-ring slot and its "full" parity
     // Spectral A operand: A[m][k] = T[j][w(m)] if pixel m sits in row h0 + k/J of the tile (block diagonal over the
     // tile's rows).  It depends on the tile only through p0 % W, so when every tile starts at column 0
     // (128 % W == 0, e.g. the shipped W = 64) it is built ONCE per CTA; otherwise it is rebuilt per tile.
@@ -401,38 +436,43 @@ k_inv_w_gemm_tc_v3(TcParams p, int B, int ntiles_per_img, const __grid_constant_
     if (p.Z != nullptr && uniform_geom && (int)blockIdx.x < ntiles) {
       int b, p0, h0, kspec, nsp;
       tile_geom(blockIdx.x, b, p0, h0, kspec, nsp);
-      build_tsp(p0, h0, kspec, nsp);                              // each thread only ever reads its own column
+      if (grp == 0) build_tsp(p0, h0, kspec, nsp);                // column tid is read by thread tid of BOTH groups
+      cvt_sync();
     }
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
       int b, p0, h0, kspec, nsp;
       tile_geom(t, b, p0, h0, kspec, nsp);
       const int pp = p0 + tid;
       const bool pvalid = pp < HW;
-      if (p.Z != nullptr && !uniform_geom) build_tsp(p0, h0, kspec, nsp);
+      if (p.Z != nullptr && !uniform_geom) {
+        cvt_sync();                                                // both groups are done with the previous tile's table
+        if (grp == 0) build_tsp(p0, h0, kspec, nsp);
+        cvt_sync();
+      }
       for (int c = 0; c < nsp + nx; ++c, ++g) {
-        const uint32_t s = g % kV3ASt, r = g % kV3Raw, q = g % kV3BSt;
+       if ((int)(g & 1) == grp) {
         if (tid == 0) TRACE(0 * 512 + g * 4 + 0);
-        if (g >= kV3ASt) ptx::mbar_wait(&bars.a_empty[s], ((g / kV3ASt) - 1) & 1);
+        if (g >= (uint32_t)NST) ptx::mbar_wait(&bars.empty[s], sph);
         if (tid == 0) TRACE(0 * 512 + g * 4 + 1);
         unsigned char* st = sA + s * a_stage;
         float v[kTcBK];
         if (kTA) ptx::tc_fence_after();
         if (c >= nsp) {
           const int cx = c - nsp;
-          ptx::mbar_wait(&bars.raw_full[r], (g / kV3Raw) & 1);
+          ptx::mbar_wait(&bars.raw_full[r], rph);
           if (tid == 0) TRACE(0 * 512 + g * 4 + 2);
           const float* rw = raw + (size_t)r * slot_f + tid;               // activation rows: dense [16][128]
 #pragma unroll
-          for (int kk = 0; kk < kTcBK; ++kk) v[kk] = (pvalid && cx * kTcBK + kk < p.K) ? rw[kk * kTcM] : 0.0f;
-          ptx::mbar_arrive(&bars.raw_empty[r]);
+          for (int kk = 0; kk < kTcBK; ++kk) v[kk] = (pvalid && cx * kTcBK + kk < p.K && !(dbg & 8)) ? rw[kk * kTcM] : 0.0f;
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&bars.raw_empty[r]);
         } else {
           // spectral chunk: A = T[j][w] on this pixel's row, B = Z rows (staged in the raw slot) -> canonical
 #pragma unroll
           for (int kk = 0; kk < kTcBK; ++kk) v[kk] = tsp[(c * kTcBK + kk) * kTcM + tid];
-          if (g >= kV3BSt) ptx::mbar_wait(&bars.b_empty[q], ((g / kV3BSt) - 1) & 1);
-          ptx::mbar_wait(&bars.raw_full[r], (g / kV3Raw) & 1);
+          ptx::mbar_wait(&bars.raw_full[r], rph);
           const float* rw = raw + (size_t)r * slot_f;                     // Z rows: dense [16][N]
-          unsigned char* sb = sB + q * b_stage;
+          unsigned char* sb = sB + s * b_stage;
           // one (n, 4 consecutive k) item = one 16-byte row of a core matrix: conflict-free LDS and STS.128
           for (int n = tid; n < npad; n += 128) {
 #pragma unroll
@@ -453,9 +493,12 @@ k_inv_w_gemm_tc_v3(TcParams p, int B, int ntiles_per_img, const __grid_constant_
               *reinterpret_cast<float4*>(sb + b_blk + off) = lo;
             }
           }
-          ptx::mbar_arrive(&bars.raw_empty[r]);
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&bars.raw_empty[r]);
         }
-        if constexpr (kTA) {
+        if (dbg & 8) {
+          ptx::tc_fence_before();
+        } else if constexpr (kTA) {
           uint32_t uh[kTcBK], ul[kTcBK];
 #pragma unroll
           for (int kk = 0; kk < kTcBK; ++kk) {
@@ -463,9 +506,9 @@ k_inv_w_gemm_tc_v3(TcParams p, int B, int ntiles_per_img, const __grid_constant_
             uh[kk] = __float_as_uint(h);
             ul[kk] = __float_as_uint(v[kk] - h);
           }
-          const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16) + s * kTcBK;
-          ptx::tmem_st16(trow + kV3TaHi, uh);
-          ptx::tmem_st16(trow + kV3TaLo, ul);
+          const uint32_t trow = tmem_base + ((uint32_t)(cwarp * 32) << 16) + s * kTcBK;
+          ptx::tmem_st16(trow + ta_hi, uh);
+          ptx::tmem_st16(trow + ta_lo, ul);
           ptx::tmem_st_wait();
           ptx::tc_fence_before();
           if (c < nsp) ptx::fence_proxy_async();                     // the spectral B block went through st.shared
@@ -483,11 +526,15 @@ k_inv_w_gemm_tc_v3(TcParams p, int B, int ntiles_per_img, const __grid_constant_
           }
           ptx::fence_proxy_async();
         }
-        ptx::mbar_arrive(&bars.a_full[s]);
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&bars.full[s]);
         if (tid == 0) TRACE(0 * 512 + g * 4 + 3);
+       }
+        if (++s == (uint32_t)NST) { s = 0; sph ^= 1; }
+        if (++r == (uint32_t)NRAW) { r = 0; rph ^= 1; }
       }
     }
-  } else if (warp == 4) {
+  } else if (warp == kK3MmaWarp) {
     if (lane == 0) {
       // ================================================================ MMA issue
       const uint32_t idesc = ptx::idesc_tf32(kTcM, npad);
@@ -496,7 +543,7 @@ k_inv_w_gemm_tc_v3(TcParams p, int B, int ntiles_per_img, const __grid_constant_
       const uint64_t a_lo0 = ptx::smem_desc_noswizzle(ptx::smem_u32(sA) + a_blk, lbo_a, sbo);
       const uint64_t b_hi0 = ptx::smem_desc_noswizzle(ptx::smem_u32(sB), lbo_b, sbo);
       const uint64_t b_lo0 = ptx::smem_desc_noswizzle(ptx::smem_u32(sB) + b_blk, lbo_b, sbo);
-      uint32_t g = 0, it = 0;
+      uint32_t g = 0, it = 0, s = 0, sph = 0;
       for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
         int b, p0, h0, kspec, nsp;
         tile_geom(t, b, p0, h0, kspec, nsp);
@@ -508,26 +555,31 @@ k_inv_w_gemm_tc_v3(TcParams p, int B, int ntiles_per_img, const __grid_constant_
         const uint32_t dcol = tmem_base + a * 256;
         const int nch = nsp + nx;
         for (int c = 0; c < nch; ++c, ++g) {
-          const uint32_t s = g % kV3ASt, q = g % kV3BSt;
           TRACE(1 * 512 + g * 4 + 0);
-          ptx::mbar_wait(&bars.a_full[s], (g / kV3ASt) & 1);
+          TRACE2(g * 10 + 0);
+          ptx::mbar_wait(&bars.full[s], sph);
           TRACE(1 * 512 + g * 4 + 1);
-          ptx::mbar_wait(&bars.b_full[q], (g / kV3BSt) & 1);
+          TRACE2(g * 10 + 1);
           TRACE(1 * 512 + g * 4 + 2);
+          TRACE2(g * 10 + 2);
           ptx::tc_fence_after();
           // only the 14-bit start-address field of a descriptor changes between stages / K steps
-          const uint64_t da = (uint64_t)((s * a_stage) >> 4), db = (uint64_t)((q * b_stage) >> 4);
+          const uint64_t da = (uint64_t)((s * a_stage) >> 4), db = (uint64_t)((s * b_stage) >> 4);
 #pragma unroll
           for (int ks = 0; ks < kTcBK / 8; ++ks) {
             const uint64_t ka = da + (uint64_t)((ks * 2 * lbo_a) >> 4), kb = db + (uint64_t)((ks * 2 * lbo_b) >> 4);
-            if constexpr (kTA) {
+            if (dbg & 1) {
+            } else if constexpr (kTA) {
               const uint32_t ta = tmem_base + s * kTcBK + ks * 8;
               if (p.single_pass) {
-                ptx::mma_tf32_ta(dcol, ta + kV3TaHi, b_hi0 + kb, idesc, (c | ks) != 0 ? 1u : 0u);
+                ptx::mma_tf32_ta(dcol, ta + ta_hi, b_hi0 + kb, idesc, (c | ks) != 0 ? 1u : 0u);
               } else {
-                ptx::mma_tf32_ta(dcol, ta + kV3TaLo, b_hi0 + kb, idesc, (c | ks) != 0 ? 1u : 0u);
-                ptx::mma_tf32_ta(dcol, ta + kV3TaHi, b_lo0 + kb, idesc, 1u);
-                ptx::mma_tf32_ta(dcol, ta + kV3TaHi, b_hi0 + kb, idesc, 1u);
+                ptx::mma_tf32_ta(dcol, ta + ta_lo, b_hi0 + kb, idesc, (c | ks) != 0 ? 1u : 0u);
+                TRACE2(g * 10 + 3 + ks * 3);
+                ptx::mma_tf32_ta(dcol, ta + ta_hi, b_lo0 + kb, idesc, 1u);
+                TRACE2(g * 10 + 4 + ks * 3);
+                ptx::mma_tf32_ta(dcol, ta + ta_hi, b_hi0 + kb, idesc, 1u);
+                TRACE2(g * 10 + 5 + ks * 3);
               }
             } else if (p.single_pass) {
               ptx::mma_tf32(dcol, a_hi0 + ka, b_hi0 + kb, idesc, (c | ks) != 0 ? 1u : 0u);
@@ -537,25 +589,28 @@ k_inv_w_gemm_tc_v3(TcParams p, int B, int ntiles_per_img, const __grid_constant_
               ptx::mma_tf32(dcol, a_hi0 + ka, b_hi0 + kb, idesc, 1u);
             }
           }
-          ptx::tc_commit(&bars.a_empty[s]);
-          ptx::tc_commit(&bars.b_empty[q]);
+          if (dbg & 16) ptx::mbar_arrive(&bars.empty[s]); else
+          ptx::tc_commit(&bars.empty[s]);
           TRACE(1 * 512 + g * 4 + 3);
+          TRACE2(g * 10 + 9);
+          if (++s == (uint32_t)NST) { s = 0; sph ^= 1; }
         }
         ptx::tc_commit(&bars.acc_full[a]);
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == kK3RawWarp) {
     if (lane == 0) {
       // ================================================================ raw ring issue (activation rows / Z rows)
-      uint32_t g = 0;
+      // The activations come from HBM (not L2): at ~1.2 us loaded latency a 3-slot ring (24 KB in flight per SM) paced
+      // the whole kernel at ~1250 cycles per chunk; the ring is now as deep as shared memory allows (up to 8 slots).
+      uint32_t g = 0, r = 0, rph = 1;
       for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
         int b, p0, h0, kspec, nsp;
         tile_geom(t, b, p0, h0, kspec, nsp);
         const int npx = (HW - p0 < kTcM) ? (HW - p0) : kTcM;
         for (int c = 0; c < nsp + nx; ++c, ++g) {
-          const uint32_t r = g % kV3Raw;
           TRACE(2 * 512 + g * 4 + 0);
-          if (g >= kV3Raw) ptx::mbar_wait(&bars.raw_empty[r], ((g / kV3Raw) - 1) & 1);
+          if (g >= (uint32_t)NRAW) ptx::mbar_wait(&bars.raw_empty[r], rph);
           TRACE(2 * 512 + g * 4 + 1);
           float* dst = raw + (size_t)r * slot_f;
           if (c < nsp) {
@@ -569,8 +624,12 @@ k_inv_w_gemm_tc_v3(TcParams p, int B, int ntiles_per_img, const __grid_constant_
             const int nk = (p.K - cx * kTcBK < kTcBK) ? (p.K - cx * kTcBK) : kTcBK;
             if (cx < ntmap_chunks) {
               // one 2-D TMA box: 16 channel rows x 128 pixels (SASS UTMALDG)
+              if (dbg & 4) {
+                ptx::mbar_arrive(&bars.raw_full[r]);
+              } else {
               ptx::mbar_arrive_expect_tx(&bars.raw_full[r], (uint32_t)kTcBK * kTcM * 4);
               ptx::tma_load_2d(dst, &tmap_x0, p0, b * p.C0 + cx * kTcBK, &bars.raw_full[r]);
+              }
             } else {
               ptx::mbar_arrive_expect_tx(&bars.raw_full[r], (uint32_t)nk * npx * 4);
               for (int kk = 0; kk < nk; ++kk) {
@@ -581,36 +640,39 @@ k_inv_w_gemm_tc_v3(TcParams p, int B, int ntiles_per_img, const __grid_constant_
             }
           }
           TRACE(2 * 512 + g * 4 + 2);
+          if (++r == (uint32_t)NRAW) { r = 0; rph ^= 1; }
         }
       }
     }
-  } else if (warp == 6) {
+  } else if (warp == kK3WgtWarp) {
     if (lane == 0) {
       // ================================================================ B ring issue (packed weight chunks)
-      uint32_t g = 0;
+      uint32_t g = 0, s = 0, sph = 1;
       for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
         int b, p0, h0, kspec, nsp;
         tile_geom(t, b, p0, h0, kspec, nsp);
         for (int c = 0; c < nsp + nx; ++c, ++g) {
-          const uint32_t q = g % kV3BSt;
-          if (g >= kV3BSt) ptx::mbar_wait(&bars.b_empty[q], ((g / kV3BSt) - 1) & 1);
+          if (g >= (uint32_t)NST) ptx::mbar_wait(&bars.empty[s], sph);
           if (c < nsp) {
-            ptx::mbar_arrive(&bars.b_full[q]);          // B of a spectral chunk is written by the convert warps
+            ptx::mbar_arrive(&bars.full[s]);            // B of a spectral chunk is written by the convert warps
+          } else if (dbg & 2) {
+            ptx::mbar_arrive(&bars.full[s]);
           } else {
-            ptx::mbar_arrive_expect_tx(&bars.b_full[q], b_stage);
-            ptx::bulk_g2s(sB + q * b_stage, p.wpack + (size_t)(c - nsp) * (b_stage / 4), b_stage, &bars.b_full[q]);
+            ptx::mbar_arrive_expect_tx(&bars.full[s], b_stage);
+            ptx::bulk_g2s(sB + s * b_stage, p.wpack + (size_t)(c - nsp) * (b_stage / 4), b_stage, &bars.full[s]);
           }
+          if (++s == (uint32_t)NST) { s = 0; sph ^= 1; }
         }
       }
     }
-  } else if (warp >= 8) {
-    // ==================================================================== epilogue: 2 warps per TMEM lane quadrant
+  } else if (warp >= 8 && warp < 8 + 4 * kK3EpiParts) {
+    // ==================================================================== epilogue: 4 warps per TMEM lane quadrant
     // Code-size discipline: the exact-erf GELU is ~40 instructions, so the column loop is NOT unrolled beyond 8
     // (a fully unrolled 32-column body was > 30 KB of SASS and ran out of the instruction cache: 270 cycles/output).
     const int quad = warp & 3, part = (warp - 8) >> 2;
     const int N = p.N;
     const int nq = (npad + 7) / 8;                                   // 8-column groups
-    const int per = (nq + kV3EpiParts - 1) / kV3EpiParts;
+    const int per = (nq + kK3EpiParts - 1) / kK3EpiParts;
     const int qbeg = (part * per < nq) ? part * per : nq, qend = (qbeg + per < nq) ? qbeg + per : nq;
     uint32_t it = 0;
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
@@ -633,6 +695,14 @@ k_inv_w_gemm_tc_v3(TcParams p, int B, int ntiles_per_img, const __grid_constant_
       ptx::mbar_wait(&bars.acc_full[a], (it / 2) & 1);
       if (tid == 256) TRACE(3 * 512 + it * 4 + 1);
       ptx::tc_fence_after();
+#ifdef PDES_TC_TRACE
+      if (p.act == 77) {                                            // debug: no epilogue work at all
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&bars.acc_empty[a]);
+        continue;
+      }
+#endif
       const uint32_t tbase = tmem_base + a * 256 + ((uint32_t)(quad * 32) << 16);
 #pragma unroll 1
       for (int qi = qbeg; qi < qend; ++qi) {
@@ -647,9 +717,13 @@ k_inv_w_gemm_tc_v3(TcParams p, int B, int ntiles_per_img, const __grid_constant_
         ptx::tmem_ld_wait();
         if (qi + 1 == qend) {                                        // accumulator fully read: hand it back to the MMA warp
           ptx::tc_fence_before();
-          ptx::mbar_arrive(&bars.acc_empty[a]);
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&bars.acc_empty[a]);
           if (tid == 256) TRACE(3 * 512 + it * 4 + 2);
         }
+#ifdef PDES_TC_TRACE
+        if (p.act == 78) { for (int e = 0; e < 8; ++e) cur[e] = nxt[e] + __uint_as_float(r[e]); continue; }   // debug: TMEM loads only
+#endif
         if (pvalid) {
           float* po = p.out + obase + (size_t)n0 * HW;
           float* pq = has_pre ? p.pre + obase + (size_t)n0 * HW : nullptr;
@@ -689,13 +763,14 @@ k_inv_w_gemm_tc_v3(TcParams p, int B, int ntiles_per_img, const __grid_constant_
       if (tid == 256) TRACE(3 * 512 + it * 4 + 3);
       if (qbeg >= qend) {                                            // no column group for this warp (N <= 8)
         ptx::tc_fence_before();
-        ptx::mbar_arrive(&bars.acc_empty[a]);                        // still only after acc_full: keeps phases in step
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&bars.acc_empty[a]);         // still only after acc_full: keeps phases in step
       }
     }
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == kK3MmaWarp) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, 512);
   }
@@ -1398,10 +1473,14 @@ int inv_w_gemm_tc_impl(const float* Z, const float* wpack, const float* x0, int 
   p.out_bs = out_bs;
   PDES_REQUIRE(out_bs >= (size_t)N * H * W, PDES_ERR_ARG, "pdes_inv_w_gemm_tc: output batch stride smaller than N*H*W");
   const int v3_rows = (kTcM + W - 1) / W + 1;
-  const bool v3_ta = tc_npad(N) <= kV3TaHi;          // A operand through tensor memory (no shared-memory A stages)
-  const bool v3_fits = (size_t)(v3_ta ? 0 : kV3ASt) * 2 * kTcM * kTcBK * 4 + (size_t)kV3BSt * 2 * tc_npad(N) * kTcBK * 4 +
-                           (size_t)kV3Raw * kTcBK * (tc_npad(N) > kTcM ? tc_npad(N) : kTcM) * 4 +
-                           (size_t)(Z != nullptr ? tc_nchunks(v3_rows * 2 * m2) : 0) * kTcBK * kTcM * 4 + 2048 <= 227 * 1024;
+  const bool v3_ta = tc_npad(N) <= kV3TaMaxN;        // A operand through tensor memory (no shared-memory A stages)
+  const int v3_nst = (v3_ta && tc_npad(N) <= 192) ? 4 : 3;
+  const size_t v3_slot = (size_t)kTcBK * (tc_npad(N) > kTcM ? tc_npad(N) : kTcM) * 4;           // bytes per raw slot
+  const size_t v3_fixed = (size_t)(v3_ta ? 0 : v3_nst) * 2 * kTcM * kTcBK * 4 + (size_t)v3_nst * 2 * tc_npad(N) * kTcBK * 4 +
+                          (size_t)(Z != nullptr ? tc_nchunks(v3_rows * 2 * m2) : 0) * kTcBK * kTcM * 4 + 2048;
+  const bool v3_fits = v3_fixed + 3 * v3_slot <= 227 * 1024;
+  int v3_nraw = v3_fits ? (int)((227 * 1024 - v3_fixed) / v3_slot) : 0;
+  if (v3_nraw > kV3MaxRaw) v3_nraw = kV3MaxRaw;
   if (g_tc_mode >= 2 && (Z == nullptr || N % 4 == 0) && v3_fits) {
     if (g_num_sms == 0) {
       int dev = 0;
@@ -1412,8 +1491,8 @@ int inv_w_gemm_tc_impl(const float* Z, const float* wpack, const float* x0, int 
     const int rawld = p.npad > kTcM ? p.npad : kTcM;
     const int rows_max = (kTcM + W - 1) / W + 1;
     const int nsp_max = (Z != nullptr) ? tc_nchunks(rows_max * 2 * m2) : 0;
-    const size_t smem3 = (size_t)(v3_ta ? 0 : kV3ASt) * 2 * kTcM * kTcBK * 4 + (size_t)kV3BSt * 2 * p.npad * kTcBK * 4 +
-                         (size_t)kV3Raw * kTcBK * rawld * 4 + (size_t)nsp_max * kTcBK * kTcM * 4 + 1024;
+    const size_t smem3 = (size_t)(v3_ta ? 0 : v3_nst) * 2 * kTcM * kTcBK * 4 + (size_t)v3_nst * 2 * p.npad * kTcBK * 4 +
+                         (size_t)v3_nraw * kTcBK * rawld * 4 + (size_t)nsp_max * kTcBK * kTcM * 4 + 1024;
     const int tiles_per_img = ceil_div(H * W, kTcM);
     const int ntiles = B * tiles_per_img;
     // 2-D tensor map over x0 viewed as [B*C0 rows][HW pixels]; used for the chunks that lie entirely inside x0 when
@@ -1432,10 +1511,21 @@ int inv_w_gemm_tc_impl(const float* Z, const float* wpack, const float* x0, int 
                                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r == CUDA_SUCCESS) ntmap_chunks = C0 / kTcBK;
     }
+#ifdef PDES_TC_TRACE
+    int v3_nst_used = v3_nst, v3_nraw_used = v3_nraw;
+    if (const char* e = getenv("PDES_V3_NST")) v3_nst_used = atoi(e);
+    if (const char* e = getenv("PDES_V3_NRAW")) v3_nraw_used = atoi(e);
+#define v3_nst v3_nst_used
+#define v3_nraw v3_nraw_used
+#endif
     auto k3 = v3_ta ? k_inv_w_gemm_tc_v3<true> : k_inv_w_gemm_tc_v3<false>;
     PDES_SET_SMEM(k3, smem3);
-    PDES_LAUNCH(k3, dim3((unsigned)(ntiles < g_num_sms ? ntiles : g_num_sms)), dim3(kV3Threads), smem3, stream, p, B,
-                tiles_per_img, tmap, ntmap_chunks);
+    PDES_LAUNCH(k3, dim3((unsigned)(ntiles < g_num_sms ? ntiles : g_num_sms)), dim3(kK3Threads), smem3, stream, p, B,
+                tiles_per_img, tmap, ntmap_chunks, v3_nst, v3_nraw);
+#ifdef PDES_TC_TRACE
+#undef v3_nst
+#undef v3_nraw
+#endif
     return check_launch("pdes_inv_w_gemm_tc(v3)");
   }
   PDES_REQUIRE(out_bs == (size_t)N * H * W, PDES_ERR_UNSUPPORTED, "pdes_inv_w_gemm_tc: strided output needs tensor-core mode >= 2");

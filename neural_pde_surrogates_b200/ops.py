@@ -420,11 +420,25 @@ class Conv1x1Function(torch.autograd.Function):
                 gw = torch.empty(N, Cin, dtype=torch.float32, device=dev)
                 gb = torch.empty(N, dtype=torch.float32, device=dev) if ctx.has_bias else None
                 ws = torch.empty(lib.pdes_wgrad_tc_workspace_floats(N, min(Cin, _C1_MAX_WG)), dtype=torch.float32, device=dev)
-                for k, (off, n) in enumerate(_ranges(Cin, _C1_MAX_WG)):
-                    _native.check(lib, lib.pdes_wgrad_tc_range(p(g), p(x), Cin, off, n, p(gw) + 4 * off, Cin, p(gb) if k == 0 else None,
-                                                               p(ws), B, N, HW, st))
-                    _counters["launches"] += 2
-                gw = gw.view_as(weight)
+                done = False
+                for cap in (_C1_MAX_WG, 128, 64):                 # the kernel's shared-memory need grows with N * channels
+                    rcs = []
+                    for k, (off, n) in enumerate(_ranges(Cin, cap)):
+                        rcs.append(lib.pdes_wgrad_tc_range(p(g), p(x), Cin, off, n, p(gw) + 4 * off, Cin, p(gb) if k == 0 else None,
+                                                           p(ws), B, N, HW, st))
+                        if rcs[-1] != _native.PDES_OK:
+                            break
+                        _counters["launches"] += 2
+                    if rcs[-1] == _native.PDES_OK:
+                        done = True
+                        break
+                    if rcs[-1] != _native.PDES_ERR_UNSUPPORTED:
+                        _native.check(lib, rcs[-1])
+                if done:
+                    gw = gw.view_as(weight)
+                else:                                              # shape outside the tensor-core kernel: cuDNN
+                    _, gw, gb = torch.ops.aten.convolution_backward(g, x, weight, [N] if ctx.has_bias else None, [1, 1], [0, 0],
+                                                                    [1, 1], False, [0, 0], 1, [False, True, ctx.has_bias])
         return gx, gw, gb
 
 

@@ -67,11 +67,12 @@ def test_large_grid(be):
 
 
 # ---- tcgen05 / TMEM path (3xTF32) ---------------------------------------------------------------------------
-@pytest.fixture(params=[1, 0], ids=["tc", "ffma"])
+@pytest.fixture(params=[2, 1, 0], ids=["tc_v3", "tc_v2", "ffma"])
 def tc_mode(request, be):
+    prev = be.lib.pdes_get_tensor_core_mode()
     be.lib.pdes_set_tensor_core_mode(request.param)
     yield request.param
-    be.lib.pdes_set_tensor_core_mode(1)
+    be.lib.pdes_set_tensor_core_mode(prev)        # the process default (2) must survive for the tests that follow
 
 
 def test_tc_weight_pack_layout(be):

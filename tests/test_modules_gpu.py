@@ -198,7 +198,7 @@ def test_conv3x3_valid_tcgen05_vs_torch(shape):
 
 
 @pytest.mark.parametrize("shape", [(2, 385, 192, 100, 68), (2, 193, 192, 96, 64), (3, 40, 75, 16, 16), (1, 192, 192, 20, 12),
-                                   (2, 27, 192, 8, 6), (1, 300, 24, 4, 4)])
+                                   (2, 27, 192, 8, 6), (1, 300, 24, 4, 4), (2, 64, 240, 16, 16), (2, 240, 200, 16, 24)])
 @pytest.mark.parametrize("bias", [True, False])
 def test_conv1x1_tcgen05_vs_torch(shape, bias):
     """U-Net / encoder / decoder 1x1 convs on the K3b + weight-gradient tensor-core kernels (3xTF32): forward and all

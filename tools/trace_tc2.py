@@ -1,4 +1,4 @@
-"""Dump the in-kernel clock trace of the persistent tcgen05 kernel (library built with -DPDES_TC_TRACE)."""
+"""MMA-issue-thread trace of the persistent K3b kernel (library built with PDES_NVCC_EXTRA=-DPDES_TC_TRACE=2)."""
 import ctypes, os, sys
 import numpy as np
 import torch
@@ -20,24 +20,21 @@ pack = torch.empty(lib.pdes_gemm_tc_pack_floats(Cin, Cout), device=dev)
 st = torch.cuda.current_stream().cuda_stream
 p = lambda t: None if t is None else t.data_ptr()
 lib.pdes_gemm_tc_pack(p(wct), Cout, Cin, Cout, p(pack), st)
-ACT = int(os.environ.get('ACT', '1'))
+ACT = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 for _ in range(3):
     lib.pdes_inv_w_gemm_tc(p(Z), p(pack), p(h), C0, p(vb), C1, p(bias), p(res), p(tab), 0, p(out), None, B, Cout, H, W, m1, m2, ACT, st)
 torch.cuda.synchronize()
 tr = np.zeros(4096, dtype=np.int64)
 lib.pdes_tc_trace_read.argtypes = [ctypes.c_void_p, ctypes.c_int]
 print("rc", lib.pdes_tc_trace_read(tr.ctypes.data, 4096))
-t0 = tr[2 * 512 + 0]
-names = {0: "conv", 1: "mma", 2: "rawi"}
-for it in range(7):
-    print("tile", it, "epi[wait_start, acc_full, released, done]", [int(tr[3*512 + it*4 + k] - t0) for k in range(4)],
-          "mma[acc_empty wait start, end]", [int(tr[3*512+256+it*2+k] - t0) for k in range(2)],
-          "conv first chunk start", int(tr[0*512 + it*16*4] - t0))
-for it in range(6):
-    print("tile", it, "tmem_ld [before, after] x3", [int(tr[3*512+300+it*8+k] - t0) for k in range(6)])
-for g in range(14, 34):
-    row = []
-    for role in (2, 0, 1):
-        vals = [int(tr[role * 512 + g * 4 + k] - t0) for k in range(4)]
-        row.append(f"{names[role]} {vals}")
-    print(g, " | ".join(row))
+t0 = tr[0]
+print("chunk: start | +a_full +b_full | 6 MMA issue deltas | +commits || period")
+prev = None
+rows = []
+for g in range(16, 80):
+    v = tr[g * 10:(g + 1) * 10] - t0
+    d = np.diff(v)
+    print(f"{g:3d}: {int(v[0]):7d} | {int(d[0]):4d} {int(d[1]):4d} | " + " ".join(f"{int(x):4d}" for x in d[2:8]) + f" | {int(d[8]):4d} || {int(v[0] - prev) if prev is not None else 0}")
+    rows.append(int(v[0] - prev) if prev is not None else 0)
+    prev = v[0]
+print('mean period', np.mean(rows[1:]), 'tile periods', [int(tr[(16*k)*10] - tr[(16*(k-1))*10]) for k in range(2, 6)])
