@@ -741,11 +741,12 @@ k_inv_w_gemm_tc_v3(TcParams p, int B, int ntiles_per_img, const __grid_constant_
               for (int e = 0; e < 8; ++e) bz[e] = 0.0f;
             }
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              float v = __uint_as_float(r[e]) + cur[e] + bz[e];
-              if (has_pre) pq[(size_t)e * HW] = v;
-              if (do_gelu) v = gelu_fast_f(v);
-              po[(size_t)e * HW] = v;
+            for (int e = 0; e < 8; e += 2) {                         // two outputs per step: packed-FFMA2 GELU
+              float2 v = make_float2(__uint_as_float(r[e]) + cur[e] + bz[e], __uint_as_float(r[e + 1]) + cur[e + 1] + bz[e + 1]);
+              if (has_pre) { pq[(size_t)e * HW] = v.x; pq[(size_t)(e + 1) * HW] = v.y; }
+              if (do_gelu) v = gelu_fast2_f(v);
+              po[(size_t)e * HW] = v.x;
+              po[(size_t)(e + 1) * HW] = v.y;
             }
           } else {
             for (int e = 0; e < 8 && n0 + e < N; ++e) {

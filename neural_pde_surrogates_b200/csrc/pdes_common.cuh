@@ -97,6 +97,54 @@ __device__ __forceinline__ float gelu_fast_f(float v) {
   const float e = 1.0f - poly * ex;
   return 0.5f * v * (1.0f + copysignf(e, x));
 }
+// acc += a * b on both halves with ONE instruction (fma.rn.f32x2, SASS FFMA2, new on sm_100).  A complex MAC
+// acc += x * w is two of them: ffma2(acc, (x.re, x.re), w); ffma2(acc, (x.im, x.im), (-w.im, w.re)); the scalar
+// broadcasts are free operand modifiers.  Same flop rate as FFMA but half the issue slots.
+__device__ __forceinline__ void ffma2(float2& acc, float2 a, float2 b) {
+#ifdef PDES_CPU_EMU
+  acc.x = fmaf(a.x, b.x, acc.x);
+  acc.y = fmaf(a.y, b.y, acc.y);
+#else
+  unsigned long long d = *reinterpret_cast<unsigned long long*>(&acc);
+  const unsigned long long aa = *reinterpret_cast<unsigned long long*>(&a), bb = *reinterpret_cast<unsigned long long*>(&b);
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(aa), "l"(bb));
+  acc = *reinterpret_cast<float2*>(&d);
+#endif
+}
+// two GELUs at once (same Abramowitz-Stegun erf as gelu_fast_f): the polynomial and the affine steps are packed
+// FFMA2 / FMUL2, only the two MUFU pairs (rcp, ex2) and the sign handling stay scalar: ~10 instructions per output
+// instead of ~16.
+__device__ __forceinline__ float2 gelu_fast2_f(float2 v) {
+#ifdef PDES_CPU_EMU
+  return make_float2(gelu_fast_f(v.x), gelu_fast_f(v.y));
+#else
+  const float2 x = make_float2(v.x * 0.70710678118654752440f, v.y * 0.70710678118654752440f);
+  const float2 ax = make_float2(fabsf(x.x), fabsf(x.y));
+  float2 den = make_float2(1.0f, 1.0f);
+  ffma2(den, make_float2(0.3275911f, 0.3275911f), ax);
+  const float2 t = make_float2(__fdividef(1.0f, den.x), __fdividef(1.0f, den.y));
+  float2 q = make_float2(0.0f, 0.0f);
+  ffma2(q, make_float2(-ax.x, -ax.y), ax);                                      // -ax^2
+  const float2 ex = make_float2(__expf(q.x), __expf(q.y));
+  float2 poly = make_float2(-1.453152027f, -1.453152027f);
+  ffma2(poly, make_float2(1.061405429f, 1.061405429f), t);
+  float2 p2 = make_float2(1.421413741f, 1.421413741f);
+  ffma2(p2, poly, t);
+  float2 p3 = make_float2(-0.284496736f, -0.284496736f);
+  ffma2(p3, p2, t);
+  float2 p4 = make_float2(0.254829592f, 0.254829592f);
+  ffma2(p4, p3, t);
+  float2 pe = make_float2(0.0f, 0.0f);
+  ffma2(pe, p4, t);                                                             // poly * t
+  float2 e = make_float2(1.0f, 1.0f);
+  ffma2(e, make_float2(-pe.x, -pe.y), ex);                                      // 1 - poly * exp(-x^2)
+  const float2 sgn = make_float2(copysignf(e.x, x.x), copysignf(e.y, x.y));
+  float2 r = make_float2(0.5f * v.x, 0.5f * v.y);
+  const float2 hv = r;
+  ffma2(r, hv, sgn);                                                            // 0.5 v (1 + erf)
+  return r;
+#endif
+}
 __device__ __forceinline__ float gelu_grad_f(float v) {
   const float cdf = 0.5f * (1.0f + erff(v * 0.70710678118654752440f));
   const float pdf = 0.39894228040143267794f * expf(-0.5f * v * v);

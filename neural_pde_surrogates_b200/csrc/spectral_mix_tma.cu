@@ -58,15 +58,6 @@ inline MixTmaGeom mix_tma_geom(int MM) {
   return g;
 }
 
-// acc += a * b on both halves with ONE instruction (SASS FFMA2, new on sm_100): a complex MAC is two of them, the
-// broadcast / swap / half-negate of the operands are free operand modifiers.
-__device__ __forceinline__ void ffma2(float2& acc, float2 a, float2 b) {
-  unsigned long long d = *reinterpret_cast<unsigned long long*>(&acc);
-  const unsigned long long aa = *reinterpret_cast<unsigned long long*>(&a), bb = *reinterpret_cast<unsigned long long*>(&b);
-  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(aa), "l"(bb));
-  acc = *reinterpret_cast<float2*>(&d);
-}
-
 struct MixTmaParams {
   float2* P;
   int B, Cred, Cn, MM, m1, m2, H, MT, ntm, red_per_split, nsplit, nstages, conj_box;
