@@ -680,7 +680,10 @@ k_inv_w_gemm_tc_v3(TcParams p, int B, int ntiles_per_img, const __grid_constant_
       tile_geom(t, b, p0, h0, kspec, nsp);
       const int pp = p0 + quad * 32 + lane;
       const bool pvalid = pp < HW;
-      const size_t obase = (size_t)b * p.out_bs + pp;
+      // 32-bit element offsets (the host guarantees B * out_bs < 2^32): one IMAD.WIDE per access instead of a 64-bit
+      // multiply-add chain, and the offset of channel n is shared by the residual load and the two stores
+      const uint32_t obase = (uint32_t)b * (uint32_t)p.out_bs + (uint32_t)pp;
+      const uint32_t uHW = (uint32_t)HW;
       const uint32_t a = it & 1;
       const bool has_res = p.res != nullptr && pvalid;
       const bool has_pre = p.pre != nullptr, do_gelu = p.act == PDES_ACT_GELU;
@@ -689,7 +692,7 @@ k_inv_w_gemm_tc_v3(TcParams p, int B, int ntiles_per_img, const __grid_constant_
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const int n = qbeg * 8 + e;
-        cur[e] = (has_res && qbeg < qend && n < N) ? __ldg(p.res + obase + (size_t)n * HW) : 0.0f;
+        cur[e] = (has_res && qbeg < qend && n < N) ? __ldg(p.res + (obase + (uint32_t)n * uHW)) : 0.0f;
       }
       if (tid == 256) TRACE(3 * 512 + it * 4 + 0);
       ptx::mbar_wait(&bars.acc_full[a], (it / 2) & 1);
@@ -710,7 +713,7 @@ k_inv_w_gemm_tc_v3(TcParams p, int B, int ntiles_per_img, const __grid_constant_
 #pragma unroll
         for (int e = 0; e < 8; ++e) {                                // prefetch the residual of the next group
           const int n = n0 + 8 + e;
-          nxt[e] = (has_res && qi + 1 < qend && n < N) ? __ldg(p.res + obase + (size_t)n * HW) : 0.0f;
+          nxt[e] = (has_res && qi + 1 < qend && n < N) ? __ldg(p.res + (obase + (uint32_t)n * uHW)) : 0.0f;
         }
         uint32_t r[8];
         ptx::tmem_ld8(tbase + (uint32_t)n0, r);
@@ -725,8 +728,9 @@ k_inv_w_gemm_tc_v3(TcParams p, int B, int ntiles_per_img, const __grid_constant_
         if (p.act == 78) { for (int e = 0; e < 8; ++e) cur[e] = nxt[e] + __uint_as_float(r[e]); continue; }   // debug: TMEM loads only
 #endif
         if (pvalid) {
-          float* po = p.out + obase + (size_t)n0 * HW;
-          float* pq = has_pre ? p.pre + obase + (size_t)n0 * HW : nullptr;
+          const uint32_t o0 = obase + (uint32_t)n0 * uHW;
+          float* const po = p.out;
+          float* const pq = p.pre;
           if (n0 + 8 <= N) {                                         // whole group valid: no per-element guards
             float bz[8];
             if (has_bias && bias_vec) {
@@ -742,19 +746,21 @@ k_inv_w_gemm_tc_v3(TcParams p, int B, int ntiles_per_img, const __grid_constant_
             }
 #pragma unroll
             for (int e = 0; e < 8; e += 2) {                         // two outputs per step: packed-FFMA2 GELU
-              float2 v = make_float2(__uint_as_float(r[e]) + cur[e] + bz[e], __uint_as_float(r[e + 1]) + cur[e + 1] + bz[e + 1]);
-              if (has_pre) { pq[(size_t)e * HW] = v.x; pq[(size_t)(e + 1) * HW] = v.y; }
+              float2 v = make_float2(cur[e] + bz[e], cur[e + 1] + bz[e + 1]);
+              ffma2(v, make_float2(__uint_as_float(r[e]), __uint_as_float(r[e + 1])), make_float2(1.0f, 1.0f));
+              const uint32_t oa = o0 + (uint32_t)e * uHW, ob = oa + uHW;
+              if (has_pre) { pq[oa] = v.x; pq[ob] = v.y; }
               if (do_gelu) v = gelu_fast2_f(v);
-              po[(size_t)e * HW] = v.x;
-              po[(size_t)(e + 1) * HW] = v.y;
+              po[oa] = v.x;
+              po[ob] = v.y;
             }
           } else {
             for (int e = 0; e < 8 && n0 + e < N; ++e) {
               float v = __uint_as_float(r[e]) + cur[e];
               if (has_bias) v += __ldg(p.bias + n0 + e);
-              if (has_pre) pq[(size_t)e * HW] = v;
+              if (has_pre) pq[o0 + (uint32_t)e * uHW] = v;
               if (do_gelu) v = gelu_fast_f(v);
-              po[(size_t)e * HW] = v;
+              po[o0 + (uint32_t)e * uHW] = v;
             }
           }
         }
@@ -1479,7 +1485,7 @@ int inv_w_gemm_tc_impl(const float* Z, const float* wpack, const float* x0, int 
   const size_t v3_slot = (size_t)kTcBK * (tc_npad(N) > kTcM ? tc_npad(N) : kTcM) * 4;           // bytes per raw slot
   const size_t v3_fixed = (size_t)(v3_ta ? 0 : v3_nst) * 2 * kTcM * kTcBK * 4 + (size_t)v3_nst * 2 * tc_npad(N) * kTcBK * 4 +
                           (size_t)(Z != nullptr ? tc_nchunks(v3_rows * 2 * m2) : 0) * kTcBK * kTcM * 4 + 2048;
-  const bool v3_fits = v3_fixed + 3 * v3_slot <= 227 * 1024;
+  const bool v3_fits = v3_fixed + 3 * v3_slot <= 227 * 1024 && (unsigned long long)B * out_bs < (1ull << 32);   // 32-bit epilogue offsets
   int v3_nraw = v3_fits ? (int)((227 * 1024 - v3_fixed) / v3_slot) : 0;
   if (v3_nraw > kV3MaxRaw) v3_nraw = kV3MaxRaw;
   if (g_tc_mode >= 2 && (Z == nullptr || N % 4 == 0) && v3_fits) {

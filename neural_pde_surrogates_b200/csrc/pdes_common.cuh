@@ -118,14 +118,19 @@ __device__ __forceinline__ float2 gelu_fast2_f(float2 v) {
 #ifdef PDES_CPU_EMU
   return make_float2(gelu_fast_f(v.x), gelu_fast_f(v.y));
 #else
-  const float2 x = make_float2(v.x * 0.70710678118654752440f, v.y * 0.70710678118654752440f);
+  const float2 zero = make_float2(0.0f, 0.0f);
+  float2 x = zero;
+  ffma2(x, v, make_float2(0.70710678118654752440f, 0.70710678118654752440f));
   const float2 ax = make_float2(fabsf(x.x), fabsf(x.y));
   float2 den = make_float2(1.0f, 1.0f);
   ffma2(den, make_float2(0.3275911f, 0.3275911f), ax);
-  const float2 t = make_float2(__fdividef(1.0f, den.x), __fdividef(1.0f, den.y));
-  float2 q = make_float2(0.0f, 0.0f);
-  ffma2(q, make_float2(-ax.x, -ax.y), ax);                                      // -ax^2
-  const float2 ex = make_float2(__expf(q.x), __expf(q.y));
+  float2 t, ex;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.x) : "f"(den.x));                   // den >= 1: no range handling needed
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.y) : "f"(den.y));
+  float2 q = zero;
+  ffma2(q, make_float2(-1.4426950408889634f * ax.x, -1.4426950408889634f * ax.y), ax);   // -ax^2 * log2(e)
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex.x) : "f"(q.x));                     // q <= 0: underflow to 0 is the right limit
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex.y) : "f"(q.y));
   float2 poly = make_float2(-1.453152027f, -1.453152027f);
   ffma2(poly, make_float2(1.061405429f, 1.061405429f), t);
   float2 p2 = make_float2(1.421413741f, 1.421413741f);
@@ -134,13 +139,14 @@ __device__ __forceinline__ float2 gelu_fast2_f(float2 v) {
   ffma2(p3, p2, t);
   float2 p4 = make_float2(0.254829592f, 0.254829592f);
   ffma2(p4, p3, t);
-  float2 pe = make_float2(0.0f, 0.0f);
+  float2 pe = zero;
   ffma2(pe, p4, t);                                                             // poly * t
   float2 e = make_float2(1.0f, 1.0f);
   ffma2(e, make_float2(-pe.x, -pe.y), ex);                                      // 1 - poly * exp(-x^2)
   const float2 sgn = make_float2(copysignf(e.x, x.x), copysignf(e.y, x.y));
-  float2 r = make_float2(0.5f * v.x, 0.5f * v.y);
-  const float2 hv = r;
+  float2 hv = zero;
+  ffma2(hv, v, make_float2(0.5f, 0.5f));
+  float2 r = hv;
   ffma2(r, hv, sgn);                                                            // 0.5 v (1 + erf)
   return r;
 #endif
