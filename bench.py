@@ -271,10 +271,10 @@ def run_ours(args):
                 "roofline": {"bound": "hbm", "kernel": "fno_block_forward chain (K1 k_dft_fwd_fast + K2 k_mix_tma + K3a k_inv_h + weight pack + K3b k_inv_w_gemm_tc_v3 on tcgen05)",
                              "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                              # dram__bytes_read+write summed over the chain's kernels, one ncu --set full capture at B=16
-                             # (profiles/r01_v4_ncu_full_block_B16.txt); above the algorithmic bytes because h is read by
+                             # (profiles/r01_v5_ncu_full_block_B16.txt); above the algorithmic bytes because h is read by
                              # K1 and again by K3b (+76 MB), the training forward also stores the pre-activation (+75 MB)
                              # and the Z / partial-sum intermediates are not fully L2-resident
-                             "traffic": 433.9e6 if B == 16 else None,
+                             "traffic": 432.0e6 if B == 16 else None,
                              "peak_source": peak_src, "alg_bytes_per_launch": block_bytes(B), "us_per_launch": fwd_us,
                              "launches_timed": len(chain["block_forward"]), "block_backward_us": bwd_us},
                 "cpu_baseline": extra.pop("cpu_baseline", None)}
