@@ -158,8 +158,37 @@ template <int N> constexpr Tw<N> make_tw() {
 
 __device__ constexpr ct::Tw<96> kTw96 = ct::make_tw<96>();
 
+// stage 1 of the fast path for the |kx| range [KB, KE): column DFT with +-kx pairing and h folding, compile-time twiddles
+template <int H, int W, int NK, int KB, int KE>
+__device__ __forceinline__ void dft_fast_stage1(const float* __restrict__ col, float (*pq)[NK][W + 1], int w) {
+  float P[KE - KB], Q[KE - KB];
+  const float v0 = col[0], vh = col[(H / 2) * W];
+#pragma unroll
+  for (int kx = KB; kx < KE; ++kx) {
+    P[kx - KB] = (kx & 1) ? (v0 - vh) : (v0 + vh);
+    Q[kx - KB] = 0.0f;
+  }
+#pragma unroll
+  for (int h = 1; h < H / 2; ++h) {
+    const float a = col[h * W], bq = col[(H - h) * W];
+    const float e = a + bq, o = a - bq;
+#pragma unroll
+    for (int kx = KB; kx < KE; ++kx) {
+      P[kx - KB] = fmaf(e, kTw96.c[(kx * h) % H], P[kx - KB]);
+      if (kx > 0) Q[kx - KB] = fmaf(o, kTw96.s[(kx * h) % H], Q[kx - KB]);
+    }
+  }
+#pragma unroll
+  for (int kx = KB; kx < KE; ++kx) {
+    pq[0][kx][w] = P[kx - KB];
+    pq[1][kx][w] = Q[kx - KB];
+  }
+}
+
+// 2*W threads per image: the two halves of the CTA take the two halves of the |kx| range in stage 1 (same shared image,
+// twice the warps per SM: the kernel is latency-bound at 2 warps per image) and share the 110 stage-2 items.
 template <int H, int W, int M1, int M2>
-__global__ void __launch_bounds__(W)
+__global__ void __launch_bounds__(2 * W)
 k_dft_fwd_fast(const float* __restrict__ x0, int C0, const float* __restrict__ x1, int C1,
                const float* __restrict__ twa_g, int nc4, const float* __restrict__ lscale, float* __restrict__ X) {
   static_assert(H == 96, "twiddle table instantiated for H = 96");
@@ -185,9 +214,9 @@ k_dft_fwd_fast(const float* __restrict__ x0, int C0, const float* __restrict__ x
   }
 #else
   (void)mbar;
-  for (int i = tid; i < H * W; i += W) img[i] = src[i];
+  for (int i = tid; i < H * W; i += 2 * W) img[i] = src[i];
 #endif
-  for (int i = tid; i < M2 * W; i += W) {
+  for (int i = tid; i < M2 * W; i += 2 * W) {
     const int l = i / W, w = i % W;
     tw2[l][w] = make_float2(__ldg(twa_g + w * nc4 + 2 * l), -__ldg(twa_g + w * nc4 + 2 * l + 1));
   }
@@ -196,37 +225,18 @@ k_dft_fwd_fast(const float* __restrict__ x0, int C0, const float* __restrict__ x
   ptx::mbar_wait(&mbar, 0);
 #endif
 
-  // ---- stage 1: column DFT with +-kx pairing and h folding, compile-time twiddles
+  // ---- stage 1 (see dft_fast_stage1)
   {
-    const float* col = img + tid;
-    float P[NK], Q[NK];
-    const float v0 = col[0], vh = col[(H / 2) * W];
-#pragma unroll
-    for (int kx = 0; kx < NK; ++kx) {
-      P[kx] = (kx & 1) ? (v0 - vh) : (v0 + vh);
-      Q[kx] = 0.0f;
-    }
-#pragma unroll
-    for (int h = 1; h < H / 2; ++h) {
-      const float a = col[h * W], bq = col[(H - h) * W];
-      const float e = a + bq, o = a - bq;
-#pragma unroll
-      for (int kx = 0; kx < NK; ++kx) {
-        P[kx] = fmaf(e, kTw96.c[(kx * h) % H], P[kx]);
-        if (kx > 0) Q[kx] = fmaf(o, kTw96.s[(kx * h) % H], Q[kx]);
-      }
-    }
-#pragma unroll
-    for (int kx = 0; kx < NK; ++kx) {
-      pq[0][kx][tid] = P[kx];
-      pq[1][kx][tid] = Q[kx];
-    }
+    constexpr int KH = (NK + 1) / 2;
+    const int w = tid & (W - 1);
+    if (tid < W) dft_fast_stage1<H, W, NK, 0, KH>(img + w, pq, w);
+    else dft_fast_stage1<H, W, NK, KH, NK>(img + w, pq, w);
   }
   __syncthreads();
 
   // ---- stage 2: row DFT of (P -+ iQ) to the M2 kept columns
   float* Xo = X + (size_t)im * (2 * M1 * M2) * 2;
-  for (int item = tid; item < NK * M2; item += W) {
+  for (int item = tid; item < NK * M2; item += 2 * W) {
     const int kxi = item / M2, l = item % M2;
     const float* pp = pq[0][kxi];
     const float* qq = pq[1][kxi];
@@ -269,7 +279,7 @@ extern "C" int pdes_dft_fwd(const float* x0, int C0, const float* x1, int C1, in
   const TableLayout t = table_layout(H, W, m1, m2);
   if (H == 96 && W == 64 && m1 == 10 && m2 == 10 && aligned16(x0) && (x1 == nullptr || aligned16(x1))) {
     auto kfast = k_dft_fwd_fast<96, 64, 10, 10>;
-    PDES_LAUNCH(kfast, dim3((unsigned)(B * (C0 + C1))), dim3(64), 0, stream, x0, C0, x1, C1, tables + t.twa, t.nc4,
+    PDES_LAUNCH(kfast, dim3((unsigned)(B * (C0 + C1))), dim3(128), 0, stream, x0, C0, x1, C1, tables + t.twa, t.nc4,
                 herm_scale ? tables + t.herm : nullptr, X);
     return check_launch("pdes_dft_fwd(fast)");
   }
