@@ -43,6 +43,9 @@ int mix_tma_splits(int B, int Cred, int Cn, int m1, int m2);
 int mix_tma_launch(bool conj, const float* Xin, const float* w1, const float* w2, float* P, int nsplit, int B, int Cred,
                    int Cn, int Cw_in, int Cw_out, int m1, int m2, int H, void* stream);
 
+int mix_dw_tma_launch(const float* X, const float* GO, float* gw1, float* gw2, int B, int Cin, int Cout, int m1, int m2,
+                      int H, void* stream);
+
 // ---- twiddle table blob layout (floats) ---------------------------------------------------------------
 // twh    [H][2]        (cos, sin)(2 pi j / H)
 // twa    [W][NC4]      K1 stage A: col 2l -> cos(2 pi l w / W), col 2l+1 -> -sin(2 pi l w / W), zero padded

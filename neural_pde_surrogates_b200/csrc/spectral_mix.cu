@@ -380,6 +380,7 @@ int pdes_mix_dw(const float* X, const float* GO, float* gw1, float* gw2, int B, 
   using namespace pdes;
   if (int e = check_mix_args("pdes_mix_dw", X, GO, gw1, gw2, B, Cin, Cout, H, m1, m2)) return e;
   const int MM = m1 * m2;
+  if (mix_dw_tma_launch(X, GO, gw1, gw2, B, Cin, Cout, m1, m2, H, stream) == PDES_OK) return PDES_OK;
   const size_t smem = (size_t)B * (kDwIR + kDwOR) * 32 * sizeof(float2);
   PDES_REQUIRE(smem <= (size_t)kMaxDynSmem, PDES_ERR_UNSUPPORTED, "pdes_mix_dw: batch %d needs %zu B of shared memory", B, smem);
   const dim3 grid((unsigned)ceil_div(2 * MM, 32), (unsigned)ceil_div(Cout, kDwOR), (unsigned)ceil_div(Cin, kDwIR));

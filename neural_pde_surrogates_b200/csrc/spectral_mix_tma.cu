@@ -32,6 +32,7 @@ int mix_tma_launch(bool, const float*, const float*, const float*, float*, int, 
                    void*) {
   return PDES_ERR_UNSUPPORTED;
 }
+int mix_dw_tma_launch(const float*, const float*, float*, float*, int, int, int, int, int, int, void*) { return PDES_ERR_UNSUPPORTED; }
 #else
 
 namespace {
@@ -176,6 +177,114 @@ k_mix_tma(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CUt
   }
 }
 
+// Weight gradient  GW[i][o][m] = sum_b conj(X[b][i][m]) * GO[b][o][m]  (written in the parameter layout), same structure:
+// one CTA = (100 modes of one weight block) x TI input channels x TO output channels, the reduction runs over the
+// samples: per sample two TMA boxes (X [TI][MT], GO [TO][MT]) land in the ring, thread = (mode, IPT x OPT channel
+// tile) keeps IPT*OPT complex accumulators and does two FFMA2 per complex MAC (conj(x) g = g.re (x.re, -x.im) +
+// g.im (x.im, x.re)).
+struct MixDwParams {
+  float2* gw1;
+  float2* gw2;
+  int B, Cin, Cout, MM, m1, m2, H, MT, ntm, nstages;
+};
+
+template <int IPT, int OPT, int GI, int GO_, int MTC>
+__global__ void __launch_bounds__(kMixTmaMaxMT * GI * GO_ + 32, 1)
+k_mix_dw_tma(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_go, MixDwParams p) {
+  constexpr int TI = IPT * GI, TO = OPT * GO_;
+  PDES_DYN_SMEM(unsigned char, smem_raw);
+  unsigned char* base = smem_raw + ((128u - (ptx::smem_u32(smem_raw) & 127u)) & 127u);
+  __shared__ __align__(8) unsigned long long full[kMixTmaMaxStages], empty[kMixTmaMaxStages];
+
+  const int MT = MTC ? MTC : p.MT, MM = p.MM;
+  const int ncomp = MT * GI * GO_;
+  const int ncomp_warps = (ncomp + 31) / 32;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int blk = blockIdx.x / p.ntm;
+  const int m0 = (blockIdx.x - blk * p.ntm) * MT;
+  const int o0 = blockIdx.y * TO, i0 = blockIdx.z * TI;
+  const int NST = p.nstages;
+  const uint32_t x_bytes = (uint32_t)TI * MT * 8, g_bytes = (uint32_t)TO * MT * 8;
+  const uint32_t stage_bytes = (x_bytes + g_bytes + 127) & ~127u;
+
+  if (tid == 0) {
+    for (int s = 0; s < NST; ++s) {
+      ptx::mbar_init(&full[s], 1);
+      ptx::mbar_init(&empty[s], ncomp_warps);
+    }
+    ptx::fence_mbar_init();
+  }
+  __syncthreads();
+
+  if (warp == ncomp_warps) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 1;
+      for (int b = 0; b < p.B; ++b) {
+        if (b >= NST) ptx::mbar_wait(&empty[s], ph);
+        unsigned char* st = base + (size_t)s * stage_bytes;
+        ptx::mbar_arrive_expect_tx(&full[s], x_bytes + g_bytes);
+        ptx::tma_load_3d(st, &tm_x, 2 * (blk * MM + m0), i0, b, &full[s]);
+        ptx::tma_load_3d(st + x_bytes, &tm_go, 2 * (blk * MM + m0), o0, b, &full[s]);
+        if (++s == NST) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp < ncomp_warps) {
+    const bool active = tid < ncomp;
+    const int m = active ? tid % MT : 0;
+    const int grp = active ? tid / MT : 0;
+    const int gi = grp % GI, go = grp / GI;
+    float2 acc[IPT][OPT];
+#pragma unroll
+    for (int t = 0; t < IPT; ++t)
+#pragma unroll
+      for (int u = 0; u < OPT; ++u) acc[t][u] = make_float2(0.0f, 0.0f);
+    const uint32_t x_off = (uint32_t)((gi * IPT) * MT + m) * 8, g_off = x_bytes + (uint32_t)((go * OPT) * MT + m) * 8;
+    int s = 0;
+    uint32_t ph = 0;
+    for (int b = 0; b < p.B; ++b) {
+      ptx::mbar_wait(&full[s], ph);
+      const unsigned char* st = base + (size_t)s * stage_bytes;
+      const float2* xs = reinterpret_cast<const float2*>(st + x_off);
+      const float2* gs = reinterpret_cast<const float2*>(st + g_off);
+      float2 xc[IPT], xw[IPT];
+#pragma unroll
+      for (int t = 0; t < IPT; ++t) {
+        const float2 x = xs[t * MT];
+        xc[t] = make_float2(x.x, -x.y);
+        xw[t] = make_float2(x.y, x.x);
+      }
+#pragma unroll
+      for (int u = 0; u < OPT; ++u) {
+        const float2 g = gs[u * MT];
+        const float2 gx = make_float2(g.x, g.x), gy = make_float2(g.y, g.y);
+#pragma unroll
+        for (int t = 0; t < IPT; ++t) {
+          ffma2(acc[t][u], gx, xc[t]);
+          ffma2(acc[t][u], gy, xw[t]);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&empty[s]);
+      if (++s == NST) { s = 0; ph ^= 1; }
+    }
+    if (active && m0 + m < MM) {
+      const bool dead = row_dead((blk * MM + m0 + m) / p.m2, p.m1, p.H);
+      float2* gw = (blk ? p.gw2 : p.gw1) + m0 + m;
+#pragma unroll
+      for (int t = 0; t < IPT; ++t) {
+        const int i = i0 + gi * IPT + t;
+        if (i >= p.Cin) continue;
+#pragma unroll
+        for (int u = 0; u < OPT; ++u) {
+          const int o = o0 + go * OPT + u;
+          if (o < p.Cout) gw[((size_t)i * p.Cout + o) * MM] = dead ? make_float2(0.f, 0.f) : acc[t][u];
+        }
+      }
+    }
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -278,6 +387,46 @@ int mix_tma_launch(bool conj, const float* Xin, const float* w1, const float* w2
   else PDES_MIXT_LAUNCH(4, 4, 4, 1);
 #undef PDES_MIXT_LAUNCH
   return check_launch(conj ? "pdes_mix_dx(tma)" : "pdes_mix_fwd(tma)");
+}
+// weight gradient of the mix; PDES_ERR_UNSUPPORTED = caller falls back to k_mix_dw
+int mix_dw_tma_launch(const float* X, const float* GO, float* gw1, float* gw2, int B, int Cin, int Cout, int m1, int m2,
+                      int H, void* stream) {
+  if (!mix_tma_shape_ok(B, Cin, Cout, m1, m2) || B < 8) return PDES_ERR_UNSUPPORTED;    // short sample loops: old kernel
+  if (!aligned16(X) || !aligned16(GO) || !aligned16(gw1) || !aligned16(gw2)) return PDES_ERR_UNSUPPORTED;
+  EncodeTiledFn enc = reinterpret_cast<EncodeTiledFn>(tensor_map_encoder());
+  if (enc == nullptr) return PDES_ERR_UNSUPPORTED;
+  constexpr int IPT = 4, OPT = 8, GI = 2, GO_ = 2, TI = IPT * GI, TO = OPT * GO_;
+  const int MM = m1 * m2;
+  const MixTmaGeom g = mix_tma_geom(MM);
+  const dim3 grid((unsigned)(2 * g.ntm), (unsigned)ceil_div(Cout, TO), (unsigned)ceil_div(Cin, TI));
+  if (grid.y > 65535 || grid.z > 65535) return PDES_ERR_UNSUPPORTED;
+  alignas(64) CUtensorMap tx, tg;
+  const cuuint64_t row = (cuuint64_t)MM * 16;                       // bytes of one [2*MM modes] complex row
+  const cuuint32_t bi = (cuuint32_t)(2 * g.MT);
+  if (!encode3(enc, &tx, X, 4 * (cuuint64_t)MM, (cuuint64_t)Cin, (cuuint64_t)B, row, row * Cin, bi, (cuuint32_t)TI, 1) ||
+      !encode3(enc, &tg, GO, 4 * (cuuint64_t)MM, (cuuint64_t)Cout, (cuuint64_t)B, row, row * Cout, bi, (cuuint32_t)TO, 1))
+    return PDES_ERR_UNSUPPORTED;
+  MixDwParams p;
+  p.gw1 = reinterpret_cast<float2*>(gw1); p.gw2 = reinterpret_cast<float2*>(gw2);
+  p.B = B; p.Cin = Cin; p.Cout = Cout; p.MM = MM; p.m1 = m1; p.m2 = m2; p.H = H; p.MT = g.MT; p.ntm = g.ntm;
+  const size_t stage = (((size_t)(TI + TO) * g.MT * 8) + 127) & ~size_t(127);
+  int nst = (int)((kMixTmaSmem - 256) / stage);
+  if (nst > kMixTmaMaxStages) nst = kMixTmaMaxStages;
+  if (nst > B) nst = B;
+  if (nst < 2) return PDES_ERR_UNSUPPORTED;
+  p.nstages = nst;
+  const size_t smem = (size_t)nst * stage + 256;
+  const unsigned threads = (unsigned)(((g.MT * GI * GO_ + 31) / 32 + 1) * 32);
+  if (g.MT == 100) {
+    auto kfn = k_mix_dw_tma<IPT, OPT, GI, GO_, 100>;
+    PDES_SET_SMEM(kfn, smem);
+    PDES_LAUNCH(kfn, grid, dim3(threads), smem, stream, tx, tg, p);
+  } else {
+    auto kfn = k_mix_dw_tma<IPT, OPT, GI, GO_, 0>;
+    PDES_SET_SMEM(kfn, smem);
+    PDES_LAUNCH(kfn, grid, dim3(threads), smem, stream, tx, tg, p);
+  }
+  return check_launch("pdes_mix_dw(tma)");
 }
 #endif  // PDES_CPU_EMU
 

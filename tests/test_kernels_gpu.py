@@ -30,6 +30,14 @@ def test_mix(be, shape):
     kc.check_mix(be, shape)
 
 
+# larger batches reach every tile configuration of the TMA-fed mix kernels (B > 8 / 5..8 / <= 4, sample tiles with
+# out-of-bounds rows, several mode tiles per weight block, dead rows) and the TMA weight-gradient kernel (B >= 8)
+@pytest.mark.parametrize("shape", [(9, 5, 1, 12, 12, 8, 3, 4), (16, 24, 1, 20, 16, 16, 4, 5), (6, 7, 0, 9, 8, 8, 2, 3),
+                                   (8, 4, 0, 6, 8, 8, 5, 2), (8, 4, 1, 6, 32, 64, 16, 16), (17, 9, 0, 17, 96, 64, 10, 10)])
+def test_mix_tma_configs(be, shape):
+    kc.check_mix(be, shape)
+
+
 @pytest.mark.parametrize("shape", kc.SMALL_SHAPES)
 def test_inverse_full(be, shape):
     kc.check_inverse(be, shape, with_gemm=True, act=1)
