@@ -305,14 +305,16 @@ k_inv_w_gemm_tc(TcParams p) {
 
 // ----------------------------------------------------------------------------------------------------------------
 // v3: persistent, warp-specialised version of the same GEMM (mode 2, default).
-//   one CTA per SM loops over 128-pixel tiles; 512 threads:
-//     warps 0-3  convert   raw ring -> hi/lo split -> canonical A stage (and, for spectral chunks, canonical B)
-//     warp  4    MMA       one thread issues tcgen05.mma into one of TWO TMEM accumulators (2 x 256 columns)
-//     warp  5    raw issue bulk async copies of activation rows / Z rows into a 3-deep raw ring
-//     warp  6    B issue   bulk async copies of the packed weight chunks into a 4-deep ring (runs up to 4 chunks
-//                          ahead, across tile boundaries, so the L2 latency of the weights is never exposed)
-//     warps 8-15 epilogue  TMEM -> registers -> bias/residual/GELU -> coalesced stores, overlapping the next tile's
-//                          main loop through the second accumulator
+//   one CTA per SM loops over 128-pixel tiles; 896 threads (see kK3* below):
+//     warps 0-7   convert   two groups taking alternate 16-channel chunks: raw ring -> hi/lo split -> the A operand in
+//                           TENSOR MEMORY (tcgen05.st) and, for the spectral chunks, the canonical B stage
+//     warps 8-23  epilogue  TMEM -> registers -> bias / residual / packed-FFMA2 GELU -> coalesced stores, overlapping
+//                           the next tile's main loop through the second accumulator
+//     warp  24    MMA       one thread issues tcgen05.mma (A from TMEM, B from shared memory) into one of TWO TMEM
+//                           accumulators and frees the stage with one tcgen05.commit
+//     warp  25    raw issue 2-D TMA boxes of activation rows / bulk copies of Z rows into a raw ring (up to 8 slots)
+//     warp  26    B issue   bulk async copies of the packed weight chunks into the stage ring, running ahead across
+//                           tile boundaries
 #ifdef PDES_TC_TRACE
 __device__ long long g_trace[4096];
 #if PDES_TC_TRACE == 2       // MMA-issue thread only: 10 stamps per chunk (start, a_full, b_full, 6 MMAs, commits)
