@@ -351,7 +351,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=16, help="per-GPU batch (config default, defaults/base.py:6)")
-    ap.add_argument("--rollout-batch", type=int, default=8)
+    ap.add_argument("--rollout-batch", type=int, default=16)
     ap.add_argument("--tf32-convs", action="store_true", help="let cuDNN use TF32 in the U-Net branch (reported separately)")
     ap.add_argument("--no-cudnn-benchmark", action="store_true",
                     help="do not let cuDNN autotune the conv algorithms of the U-Net branch (default: autotune on)")
