@@ -2,7 +2,7 @@
 """Benchmark of the B200-native U-FNO hot path (contract: see the task statement / DESIGN.md §Measurement).
 
     python bench.py --gpus N --steps K --warmup W            # our arm (one rank per GPU under torchrun for N>1)
-    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port) on the host cores
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU path on the host cores
 
 Workload (`config.workload`): cfg_twophase_ufno -- U-FNO, 3 blocks, width 192, modes 10x10, grid 96x64, tw 25,
 Cin = 193 (mask-only conditioning), per-GPU batch 16, fp32 (cuDNN TF32 off), push-forward unroll u=0, Adam.
@@ -10,8 +10,13 @@ A step = one optimizer step (forward + backward + gradient all-reduce + Adam) on
 `value`   : training samples/s, whole job, inputs already resident in HBM.
 `e2e`     : the same through the public trainer API with the batch in pinned HOST memory (H2D of the windows and
             D2H of the loss inside the timed region).
-`roofline`: the fused spectral-block forward chain (K1+K2+K3a+K3b), algorithmic bytes / CUDA-event time measured
-            in situ during the timed steps, against the measured HBM copy bandwidth.
+`roofline`: the fused spectral-block forward chain, algorithmic bytes / CUDA-event time measured in situ during the
+            timed steps, against the measured HBM copy bandwidth.
+
+Multi-GPU: EVERY leg below runs on EVERY rank with matching collectives (round 1 ran the secondary legs on rank 0
+with a data-parallel trainer and dead-locked in its all-reduce); the only rank-0-only work is collective-free (the
+CPU baseline and printing) while the other ranks wait in one final barrier.  The control flow is exercised on CPU
+by tests/test_bench_flow.py (gloo, world_size 2) through the `Harness` seam.
 """
 from __future__ import annotations
 
@@ -23,19 +28,38 @@ import subprocess
 import sys
 import threading
 import time
+from dataclasses import dataclass
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 import torch  # noqa: E402
 
-H, W, TW, WIDTH, MODES, BLOCKS, NCOND = 96, 64, 25, 192, 10, 3, 1
+
+@dataclass
+class Workload:
+    """Shape of the benchmarked model; the default is cfg_twophase_ufno.py:51-89 on the twophase snapshot shape."""
+    H: int = 96
+    W: int = 64
+    tw: int = 25
+    width: int = 192
+    modes: int = 10
+    blocks: int = 3
+    ncond: int = 1
+    name: str = "cfg_twophase_ufno"
+
+    def block_bytes(self, B):
+        """Algorithmic bytes of one fused U-FNO block tail, fp32 (SURVEY.md §8d / BASELINE.md §3)."""
+        Cin, Cout = self.width + self.ncond, self.width
+        spec = 4 * B * Cin * self.H * self.W + 16 * Cin * Cout * self.modes * self.modes + 4 * B * Cout * self.H * self.W
+        return spec + 4 * B * Cout * self.H * self.W + 4 * Cout * Cin + 4 * Cout
 
 
-def block_bytes(B, Cin=WIDTH + NCOND, Cout=WIDTH):
-    """Algorithmic bytes of one fused U-FNO block tail, fp32 (SURVEY.md §8d / BASELINE.md §3)."""
-    spec = 4 * B * Cin * H * W + 16 * Cin * Cout * MODES * MODES + 4 * B * Cout * H * W
-    return spec + 4 * B * Cout * H * W + 4 * Cout * Cin + 4 * Cout
+WL = Workload()
+
+
+def block_bytes(B, wl: Workload = WL):
+    return wl.block_bytes(B)
 
 
 def measured_peak():
@@ -44,6 +68,22 @@ def measured_peak():
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def recorded_traffic(B):
+    """dram__bytes_read+write of the forward chain from the newest committed ncu --set full capture
+    (profiles/*_chain_traffic.json, written by tools/ncu_summary.py); None when no capture matches this batch."""
+    try:
+        files = sorted(f for f in os.listdir(os.path.join(ROOT, "profiles")) if f.endswith("_chain_traffic.json"))
+        if not files:
+            return None, None
+        with open(os.path.join(ROOT, "profiles", files[-1])) as f:
+            rec = json.load(f)
+        if int(rec.get("batch", -1)) != B:
+            return None, None
+        return float(rec["dram_bytes_per_chain"]), f"profiles/{files[-1]}"
+    except Exception:
+        return None, None
 
 
 class ClockSampler:
@@ -83,125 +123,205 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
-def synthetic_batch(B, pde, device, gen):
+def synthetic_batch(B, pde, gen, wl: Workload = WL):
     """SURVEY.md §8d synthetic inputs: u ~ U(0.1, 0.6), Bernoulli(0.1) obstacle mask, empty static conditioning."""
-    u = torch.rand(B, 1, TW, H, W, generator=gen) * 0.5 + 0.1
-    labels = torch.rand(B, 1, TW, H, W, generator=gen) * 0.5 + 0.1
-    mask = (torch.rand(B, 1, H, W, generator=gen) < 0.1).float()
+    u = torch.rand(B, 1, wl.tw, wl.H, wl.W, generator=gen) * 0.5 + 0.1
+    labels = torch.rand(B, 1, wl.tw, wl.H, wl.W, generator=gen) * 0.5 + 0.1
+    mask = (torch.rand(B, 1, wl.H, wl.W, generator=gen) < 0.1).float()
     pos = pde.x[None].repeat(B, 1, 1, 1)
     return u, labels, mask, pos
 
 
-def build(device, seed=42, hidden_blocks=BLOCKS):
+def build(device, wl: Workload = WL, seed=42, processor="UFNO"):
     import neural_pde_surrogates_b200 as npb
     torch.manual_seed(seed)
-    pde = npb.TwoPhasePDE(H, W)
-    model = npb.build_twophase_model(pde=pde, hidden_features=WIDTH, fno_modes=MODES, hidden_blocks=hidden_blocks)
+    pde = npb.TwoPhasePDE(wl.H, wl.W)
+    model = npb.build_twophase_model(pde=pde, hidden_features=wl.width, fno_modes=wl.modes, hidden_blocks=wl.blocks,
+                                     processor=processor)
     return model.to(device), pde
 
 
+def workload_config(B, n, wl: Workload = WL):
+    return {"workload": f"{wl.name} train step (U-FNO x{wl.blocks}, width {wl.width}, modes {wl.modes}x{wl.modes}, grid {wl.H}x{wl.W}, "
+                        f"tw {wl.tw}, Cin {wl.width + wl.ncond}, Adam, unroll u=0)",
+            "per_gpu_batch": B, "global_batch": B * n, "parallelism": f"dp{n}", "grid": [wl.H, wl.W],
+            "precision": "fp32 (cuDNN TF32 off, cudnn.benchmark on; spectral block 3xTF32 split on tcgen05 = fp32-faithful)",
+            "l2_policy": "inputs+weights+activations per step (~1 GB) exceed the 126 MB L2; no explicit flush"}
+
+
 # ------------------------------------------------------------------------------------------------ reference arm
-def run_reference(args):
-    """The reference's own algorithm on the host cores: the CPU port of the same model (oracle/torch_port.py; the
-    unmodified reference cannot travel to the GPU box).  Bounded sample of the same workload per step."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
+def reference_stepper(B, wl: Workload = WL):
+    """(step_fn, kind, description): one optimizer step of the reference's own CPU implementation at batch B.
+
+    kind "reference": the UNMODIFIED reference (oracle/_ref or /root/reference): its `models.activation_wrapper` model
+    built from the cfg_twophase_ufno model dict and its own `AutoregressivePushforwardTrainer.train_step`
+    (autoregressivepushforwardtrainer.py:43-163) + backward + Adam step (trainers/base.py:490-493) on whole synthetic
+    trajectories.  kind "port": oracle/torch_port.py swapped into the product modules (only when no copy of the
+    reference is present)."""
+    from oracle import reference_loader as rl
+    gen = torch.Generator().manual_seed(1)
+    if rl.reference_available():
+        from types import SimpleNamespace
+        from neural_pde_surrogates_b200.shell import twophase_model_kwargs
+        ref = rl.load_reference()
+        pde = rl.twophase_pde(ref, wl.H, wl.W)
+        torch.manual_seed(42)
+        kw = twophase_model_kwargs("UFNO", hidden_features=wl.width, fno_modes=wl.modes, hidden_blocks=wl.blocks)
+        model = ref.models.activation_wrapper(model_class="EncProcDec", **kw, pde=pde)
+        T = ref.trainer.AutoregressivePushforwardTrainer
+        tr = T.__new__(T)                                   # the trainer without its dataset / dataloader plumbing
+        from common.data_creator import DataCreator
+        from common.interfaces import D
+        nt = 3 * wl.tw                                      # shortest trajectory train_step accepts (one window start)
+        tr.config = SimpleNamespace(device="cpu", batch_size=B, lr_step_interval=25, unrolling=8, process_settings={},
+                                    base_resolution=(nt, wl.H, wl.W), time_window=wl.tw)
+        tr.model, tr.criterion = model, torch.nn.MSELoss(reduction="sum")
+        tr.data = SimpleNamespace(pde=pde, data_interface=D.sim2d)
+        tr.data_creator = DataCreator(pde=pde, neighbors=3, time_window=wl.tw, t_resolution=nt, x_resolution=wl.H)
+        opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+        u_super = torch.rand(B, 1, nt, wl.H, wl.W, generator=gen) * 0.5 + 0.1
+        mask = (torch.rand(B, 1, wl.H, wl.W, generator=gen) < 0.1).float()
+        pos = pde.x[None].repeat(B, 1, 1, 1)
+        batch = (torch.empty(0), u_super, pos, torch.empty(B, 0), torch.empty(0), mask)
+
+        def step():
+            opt.zero_grad()
+            loss, _ = tr.train_step(batch, 0, 0, None)     # epoch 0 => unroll u = 0
+            loss.backward()
+            opt.step()
+            return float(loss.detach())
+        return step, "reference", (f"unmodified reference ({rl.reference_kind()}: {os.path.relpath(rl.REFERENCE_SRC, ROOT)}): "
+                                   "activation_wrapper(EncProcDec(UFNO)) + its own train_step + backward + Adam")
     from neural_pde_surrogates_b200.trainer import AutoregressivePushforwardTrainer
     from oracle.torch_port import cpu_port
+    model, pde = build("cpu", wl)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+    tr = AutoregressivePushforwardTrainer(model, pde, optimizer=opt, device="cpu", batch_size=B)
+    u, labels, mask, pos = synthetic_batch(B, pde, gen, wl)
+
+    def step():
+        with cpu_port():
+            loss, _ = tr.train_step_windows(u, labels, pos, torch.empty(B, 0), mask)
+            tr.optimizer_step(loss)
+        return float(loss.detach())
+    return step, "port", "CPU port of the reference algorithm (oracle/torch_port.py: torch.fft + einsum + conv)"
+
+
+def run_reference(args, wl: Workload = WL):
+    """The reference's own CPU implementation of the path on the host cores, same config (per-GPU batch) as our arm.
+    Only rank 0 works; the other ranks of a torchrun launch exit 0."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    model, pde = build("cpu")
-    opt = torch.optim.Adam(model.parameters(), lr=1e-4)
-    gen = torch.Generator().manual_seed(1)
-    Bs = 4
-    with cpu_port():
-        while True:
-            tr = AutoregressivePushforwardTrainer(model, pde, optimizer=opt, device="cpu", batch_size=Bs)
-            u, labels, mask, pos = synthetic_batch(Bs, pde, "cpu", gen)
-            t0 = time.perf_counter()
-            loss, _ = tr.train_step_windows(u, labels, pos, torch.empty(Bs, 0), mask)
-            tr.optimizer_step(loss)
-            t_probe = time.perf_counter() - t0
-            if Bs == 1 or t_probe * (args.steps + args.warmup) < 200:
-                break
-            Bs //= 2
-        for _ in range(max(args.warmup - 1, 0)):
-            loss, _ = tr.train_step_windows(u, labels, pos, torch.empty(Bs, 0), mask)
-            tr.optimizer_step(loss)
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            loss, _ = tr.train_step_windows(u, labels, pos, torch.empty(Bs, 0), mask)
-            tr.optimizer_step(loss)
-            float(loss.detach())
-        dt = time.perf_counter() - t0
-    v = Bs * args.steps / dt
-    sample = f"{args.steps} optimizer steps of cfg_twophase_ufno at batch {Bs} (fwd+bwd+Adam, u=0) on the host CPU"
+    B = args.batch
+    step, kind, what = reference_stepper(B, wl)
+    t0 = time.perf_counter()
+    step()                                                   # first call: allocations, oneDNN primitive creation
+    t_probe = time.perf_counter() - t0
+    budget = 280.0                                           # the whole run must end within a few minutes
+    if B > 1 and t_probe * (args.steps + args.warmup) > budget:
+        B = max(1, int(B * budget / (t_probe * (args.steps + args.warmup))))   # bounded sample: smaller batch per step
+        step, kind, what = reference_stepper(B, wl)
+        step()
+    for _ in range(max(args.warmup - 1, 0)):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    v = B * args.steps / dt
+    sample = f"{args.steps} optimizer steps of {wl.name} at batch {B} (fwd+bwd+Adam, u=0) on the host CPU; {what}"
     line = {"impl": "reference", "metric": "train_samples_per_s", "value": v, "unit": "samples/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(Bs, 1),
-            "cpu_baseline": {"value": v, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+            "config": workload_config(B, 1, wl),
+            "cpu_baseline": {"value": v, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": kind, "sample": sample},
             "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
-def workload_config(B, n):
-    return {"workload": "cfg_twophase_ufno train step (U-FNO x3, width 192, modes 10x10, grid 96x64, tw 25, Cin 193, Adam, unroll u=0)",
-            "per_gpu_batch": B, "global_batch": B * n, "parallelism": f"dp{n}", "grid": [H, W], "precision": "fp32 (cuDNN TF32 off, cudnn.benchmark on; spectral block 3xTF32 split on tcgen05 = fp32-faithful)",
-            "l2_policy": "inputs+weights+activations per step (~1 GB) exceed the 126 MB L2; no explicit flush"}
-
-
-def cpu_baseline_sample():
-    """Oracle port timed on the host cores on a bounded sample (one warm-up + timed steps at batch 4)."""
-    from neural_pde_surrogates_b200.trainer import AutoregressivePushforwardTrainer
-    from oracle.torch_port import cpu_port
+def cpu_baseline_sample(B, wl: Workload = WL, seconds=14.0):
+    """The reference's CPU implementation timed on the host cores on a bounded sample (one warm-up + >= 2 timed steps)."""
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    model, pde = build("cpu")
-    opt = torch.optim.Adam(model.parameters(), lr=1e-4)
-    gen = torch.Generator().manual_seed(1)
-    Bs, n = 4, 0
-    tr = AutoregressivePushforwardTrainer(model, pde, optimizer=opt, device="cpu", batch_size=Bs)
-    u, labels, mask, pos = synthetic_batch(Bs, pde, "cpu", gen)
-    with cpu_port():
-        loss, _ = tr.train_step_windows(u, labels, pos, torch.empty(Bs, 0), mask)
-        tr.optimizer_step(loss)
-        t0 = time.perf_counter()
-        while n < 2 or (time.perf_counter() - t0 < 12 and n < 8):
-            loss, _ = tr.train_step_windows(u, labels, pos, torch.empty(Bs, 0), mask)
-            tr.optimizer_step(loss)
-            n += 1
-        dt = time.perf_counter() - t0
-    return {"value": Bs * n / dt, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{n} optimizer steps of the same model at batch {Bs} with the CPU port of the reference algorithm "
-                      f"(oracle/torch_port.py: torch.fft + einsum + conv), {dt:.1f} s"}
+    step, kind, what = reference_stepper(B, wl)
+    step()
+    n, t0 = 0, time.perf_counter()
+    while n < 2 or (time.perf_counter() - t0 < seconds and n < 8):
+        step()
+        n += 1
+    dt = time.perf_counter() - t0
+    return {"value": B * n / dt, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": kind,
+            "sample": f"{n} optimizer steps of the same model at batch {B}, {dt:.1f} s; {what}"}
 
 
 # ------------------------------------------------------------------------------------------------ our arm
-def run_ours(args):
-    import torch.distributed as dist
+class Harness:
+    """Device / process-group / timing seam.  The CUDA implementation is the product benchmark; tests substitute a
+    CPU + gloo implementation to exercise the multi-rank control flow of `run_legs`."""
+
+    def __init__(self):
+        import torch.distributed as dist
+        from neural_pde_surrogates_b200 import dp
+        self.dist = dist
+        self.rank, self.world, self.local = dp.init_distributed()
+        self.dev = torch.device("cuda", self.local)
+        torch.cuda.set_device(self.dev)
+        self.graphs = True                                   # CUDA-graph replay available
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(self, x: float) -> float:
+        if self.world > 1:
+            t = torch.tensor([x], device=self.dev, dtype=torch.float64)
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+            return float(t.item())
+        return float(x)
+
+    def min_over_ranks(self, x: float) -> float:
+        return -self.max_over_ranks(-x)
+
+    def timed(self, fn, steps) -> float:
+        """ms for `steps` calls: CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks."""
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        self.barrier()
+        return self.max_over_ranks(e0.elapsed_time(e1))
+
+    def pin(self, t):
+        return t.pin_memory()
+
+    def clock_sampler(self):
+        return ClockSampler(self.local)
+
+    def finish(self):
+        if self.world > 1:
+            self.dist.barrier()
+            self.dist.destroy_process_group()
+
+
+def leg_train(hx: Harness, args, wl: Workload):
+    """Headline: `steps` optimizer steps, inputs resident (value) and from pinned host memory (e2e)."""
     from neural_pde_surrogates_b200 import dp, ops
     from neural_pde_surrogates_b200.trainer import AutoregressivePushforwardTrainer
-
-    rank, world, local = dp.init_distributed()
-    if world != args.gpus and rank == 0:
-        print(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}", file=sys.stderr)
-    dev = torch.device("cuda", local)
-    torch.cuda.set_device(dev)
-    torch.backends.cudnn.allow_tf32 = args.tf32_convs
-    torch.backends.cuda.matmul.allow_tf32 = False
-    torch.backends.cudnn.benchmark = not args.no_cudnn_benchmark
-    B = args.batch
-
-    model, pde = build(dev)
+    dev, B = hx.dev, args.batch
+    model, pde = build(dev, wl)
     opt = torch.optim.Adam(model.parameters(), lr=1e-4)                 # defaults/optimizer.py:4-7
-    tr = AutoregressivePushforwardTrainer(model, pde, optimizer=opt, device=dev, batch_size=B)
-    if world > 1:
+    tr = AutoregressivePushforwardTrainer(model, pde, optimizer=opt, device=dev, batch_size=B,
+                                          base_resolution=(501, wl.H, wl.W))
+    if hx.world > 1:
         dp.make_data_parallel(tr, seed=42)
-    gen = torch.Generator().manual_seed(1234 + rank)
-    u, labels, mask, pos = synthetic_batch(B, pde, dev, gen)
-    u_h, labels_h = u.pin_memory(), labels.pin_memory()                  # host copies for the e2e leg
+    gen = torch.Generator().manual_seed(1234 + hx.rank)
+    u, labels, mask, pos = synthetic_batch(B, pde, gen, wl)
+    u_h, labels_h = hx.pin(u), hx.pin(labels)                            # host copies for the e2e leg
     u_d, labels_d, mask_d, pos_d = u.to(dev), labels.to(dev), mask.to(dev), pos.to(dev)
     cond = torch.empty(B, 0, device=dev)
 
@@ -217,147 +337,229 @@ def run_ours(args):
         tr.optimizer_step(loss)
         return float(loss.detach())                                               # D2H read of the step's result
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, steps, sampler=None):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
-            fn()
-        e1.record()
-        barrier()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms
-
-    for _ in range(max(args.warmup, 3)):
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
         step_resident()
     ops.reset_counters()
     ops.enable_timing(True)
-    with ClockSampler(local) as clocks:
-        ms = timed(step_resident, args.steps)
+    with hx.clock_sampler() as clocks:
+        ms = hx.timed(step_resident, args.steps)
     ops.enable_timing(False)
     launches = ops.counters()["launches"]
     chain = ops.collect_timings()
     for _ in range(2):
         step_e2e()
-    ms_e2e = timed(step_e2e, args.steps)
-
-    value = B * world * args.steps / (ms * 1e-3)
-    e2e_value = B * world * args.steps / (ms_e2e * 1e-3)
-
-    extra = {}
-    if rank == 0 and not args.no_extras:
-        extra = extras(tr, model, pde, dev, B, args)
-    if rank == 0:
-        peak, peak_src = measured_peak()
-        fwd_us = statistics.mean(chain["block_forward"]) * 1e3 if chain["block_forward"] else float("nan")
-        bwd_us = statistics.mean(chain["block_backward"]) * 1e3 if chain["block_backward"] else float("nan")
-        ach = block_bytes(B) / (fwd_us * 1e-6) / 1e9
-        line = {"metric": "train_samples_per_s", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
-                "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(B, world),
-                "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(u_h.numel() * 4 + labels_h.numel() * 4),
-                        "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
-                "gpu_launches": launches,
-                "clocks": clocks.summary(),
-                "roofline": {"bound": "hbm", "kernel": "fno_block_forward chain (K1 k_dft_fwd_fast + K2 k_mix_tma + K3a k_inv_h + weight pack + K3b k_inv_w_gemm_tc_v3 on tcgen05)",
-                             "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                             # dram__bytes_read+write summed over the chain's kernels, one ncu --set full capture at B=16
-                             # (profiles/r01_v5_ncu_full_block_B16.txt); above the algorithmic bytes because h is read by
-                             # K1 and again by K3b (+76 MB), the training forward also stores the pre-activation (+75 MB)
-                             # and the Z / partial-sum intermediates are not fully L2-resident
-                             "traffic": 432.0e6 if B == 16 else None,
-                             "peak_source": peak_src, "alg_bytes_per_launch": block_bytes(B), "us_per_launch": fwd_us,
-                             "launches_timed": len(chain["block_forward"]), "block_backward_us": bwd_us},
-                "cpu_baseline": extra.pop("cpu_baseline", None)}
-        line.update(extra)
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    ms_e2e = hx.timed(step_e2e, args.steps)
+    return {"trainer": tr, "model": model, "pde": pde, "ms": ms, "ms_e2e": ms_e2e, "launches": launches, "chain": chain,
+            "clocks": clocks.summary(), "warmup": warm,
+            "h2d": int(u_h.numel() * 4 + labels_h.numel() * 4), "value": B * hx.world * args.steps / (ms * 1e-3),
+            "e2e_value": B * hx.world * args.steps / (ms_e2e * 1e-3)}
 
 
-def extras(tr, model, pde, dev, B, args):
-    """Secondary numbers of the same run: rollout steps/s (eager and CUDA-graph), block micro-benchmark, CPU baseline."""
-    out = {}
-    model.eval()
-    Br = args.rollout_batch
-    gen = torch.Generator().manual_seed(7)
-    u, _, mask, pos = synthetic_batch(Br, pde, dev, gen)
+def leg_rollout(hx: Harness, args, wl: Workload, tr, model, pde):
+    """Config #4: 50-step autoregressive rollout, trajectories sharded over the ranks, NO collective in the timed
+    region (the max over ranks of the per-rank time is taken afterwards)."""
+    from neural_pde_surrogates_b200 import dp
+    dev = hx.dev
+    n_total = args.rollout_batch * hx.world
+    mine = dp.shard_trajectories(n_total, hx.rank, hx.world)
+    Br = max(len(mine), 1)
+    gen = torch.Generator().manual_seed(7 + hx.rank)
+    u, _, mask, pos = synthetic_batch(Br, pde, gen, wl)
     u, pos = u.to(dev), pos.to(dev)
     mask = torch.zeros_like(mask).to(dev)                                 # twophase_no_obstacle: mask all zeros
     cond = torch.empty(Br, 0, device=dev)
-    nsteps = 50
-    kw = dict(compute_loss=False, include_data=True, nr_gt_steps=1, t_res=TW * (nsteps + 1), spatial_conditioning=mask,
+    nsteps = args.rollout_steps
+    kw = dict(compute_loss=False, include_data=True, nr_gt_steps=1, t_res=wl.tw * (nsteps + 1), spatial_conditioning=mask,
               use_bc=False, divide_by_t=False)
-    res = {}
-    with torch.no_grad():
-        for graph in (False, True):
-            tr.simulate(u, cond, pos, graph=graph, **dict(kw, t_res=TW * 3))      # warm-up (and graph capture)
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            preds = tr.simulate(u, cond, pos, graph=graph, **kw)
-            e1.record()
-            torch.cuda.synchronize()
-            res["graph" if graph else "eager"] = Br * nsteps / (e0.elapsed_time(e1) * 1e-3)
-        finite = bool(torch.isfinite(preds[-1]).all())
-    out["rollout"] = {"metric": "rollout_trajectory_steps_per_s", "steps": nsteps, "trajectories": Br,
-                      "eager": res["eager"], "cuda_graph": res["graph"], "finite": finite,
-                      "note": "one step = one model application advancing 25 frames; state stays in HBM"}
+    res, ok, finite, err = {}, 1.0, True, ""
+    modes = ("eager", "graph") if hx.graphs else ("eager",)
+    model.eval()
+    try:
+        with torch.no_grad():
+            for mode in modes:
+                tr.simulate(u, cond, pos, graph=(mode == "graph"), **dict(kw, t_res=wl.tw * 3))   # warm-up / capture
+                res[mode] = hx.timed(lambda: tr.simulate(u, cond, pos, graph=(mode == "graph"), **kw), 1)
+            preds = tr.simulate(u, cond, pos, graph=hx.graphs, **dict(kw, t_res=wl.tw * 3))
+            finite = bool(torch.isfinite(preds[-1]).all())
+    except Exception as exc:                                              # noqa: BLE001  (no collective was pending)
+        ok, err = 0.0, repr(exc)[:200]
+        for mode in modes:                                                 # keep the collectives of hx.timed matched
+            if mode not in res:
+                res[mode] = hx.timed(lambda: None, 1)
     model.train()
-    # push-forward training step with the maximum unroll of the shipped config (u = 8 no-grad applications feeding one
-    # differentiable application, autoregressivepushforwardtrainer.py:115-144); the headline `value` is u = 0
-    ut, lt, mt, pt = synthetic_batch(B, pde, dev, torch.Generator().manual_seed(11))
+    all_ok = hx.min_over_ranks(ok) > 0.5
+    out = {"metric": "rollout_trajectory_steps_per_s", "steps": nsteps, "trajectories": n_total,
+           "trajectories_per_gpu": args.rollout_batch, "n_gpus": hx.world, "sharding": "trajectories, no collective",
+           "finite": finite, "note": "one step = one model application advancing 25 frames; state stays in HBM; "
+                                     "time = max over ranks"}
+    if all_ok:
+        out["eager"] = n_total * nsteps / (res["eager"] * 1e-3)
+        if "graph" in res:
+            out["cuda_graph"] = n_total * nsteps / (res["graph"] * 1e-3)
+    else:
+        out["error"] = err or "failed on another rank"
+    return out
+
+
+def leg_unroll8(hx: Harness, args, wl: Workload, tr, pde):
+    """The same optimizer step with the maximum push-forward unroll of the shipped config (8 no-grad applications + 1
+    with grad, autoregressivepushforwardtrainer.py:115-144).  Runs on ALL ranks with the data-parallel trainer."""
+    dev, B = hx.dev, args.batch
+    ut, lt, mt, pt = synthetic_batch(B, pde, torch.Generator().manual_seed(11 + hx.rank), wl)
     ut, lt, mt, pt = ut.to(dev), lt.to(dev), mt.to(dev), pt.to(dev)
     condt = torch.empty(B, 0, device=dev)
 
     def step_u8():
-        loss, _ = tr.train_step_windows(ut, lt, pt, condt, mt, unrolled=8, next_labels=lambda k: lt)
+        loss, _ = tr.train_step_windows(ut, lt, pt, condt, mt, unrolled=args.unroll, next_labels=lambda k: lt)
         tr.optimizer_step(loss)
-    try:                                                         # a secondary number must never cost the headline line
-        for _ in range(2):
-            step_u8()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        n8 = 3
-        e0.record()
-        for _ in range(n8):
-            step_u8()
-        e1.record()
-        torch.cuda.synchronize()
-        ms8 = e0.elapsed_time(e1) / n8
-        out["train_unroll8"] = {"metric": "train_samples_per_s", "unroll": 8, "value": B / (ms8 * 1e-3), "ms_per_step": ms8,
-                                "note": "per GPU; 8 no-grad model applications + 1 with grad per optimizer step"}
-    except Exception as exc:                                     # noqa: BLE001
-        out["train_unroll8"] = {"error": repr(exc)[:200]}
-    if not args.no_cpu_baseline:
-        out["cpu_baseline"] = cpu_baseline_sample()
+    for _ in range(2):
+        step_u8()
+    n8 = 3
+    ms8 = hx.timed(step_u8, n8) / n8
+    return {"metric": "train_samples_per_s", "unroll": args.unroll, "value": B * hx.world / (ms8 * 1e-3), "ms_per_step": ms8,
+            "n_gpus": hx.world, "note": f"whole job; {args.unroll} no-grad model applications + 1 with grad per optimizer step"}
+
+
+def leg_other_configs(hx: Harness, args):
+    """Secondary single-GPU numbers for BASELINE.json configs #2 and #5 (parity cases, not the headline)."""
+    from neural_pde_surrogates_b200.trainer import AutoregressivePushforwardTrainer
+    out = {}
+    dev = hx.dev
+
+    def train_rate(wl, processor, B, steps=4, tf32=False):
+        torch.backends.cudnn.allow_tf32 = tf32
+        model, pde = build(dev, wl, processor=processor)
+        opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+        tr = AutoregressivePushforwardTrainer(model, pde, optimizer=opt, device=dev, batch_size=B,
+                                              base_resolution=(501, wl.H, wl.W))
+        u, labels, mask, pos = (t.to(dev) for t in synthetic_batch(B, pde, torch.Generator().manual_seed(5), wl))
+        cond = torch.empty(B, 0, device=dev)
+
+        def step():
+            loss, pred = tr.train_step_windows(u, labels, pos, cond, mask)
+            tr.optimizer_step(loss)
+            return pred
+        for _ in range(3):
+            step()
+        ms = hx.timed(step, steps) / steps
+        with torch.no_grad():
+            pred = model(u, cond=cond, bc=None, pos=pos, t_cond=None, spatial_cond=mask).clone()
+        del tr, opt
+        return B / (ms * 1e-3), ms, pred, model
+
+    try:                                                                  # config #2: cfg_twophase_ufno_fno, 1 GPU
+        wl2 = Workload(name="cfg_twophase_ufno_fno")
+        proc = [dict(object="FNO", hidden_blocks=1), dict(object="UFNO", hidden_blocks=1)]
+        v, ms, _, _ = train_rate(wl2, proc, args.batch)
+        out["config2_ufno_fno"] = {"metric": "train_samples_per_s", "value": v, "ms_per_step": ms, "per_gpu_batch": args.batch,
+                                   "processor": "[FNO(hidden_blocks=1), UFNO(hidden_blocks=1)], width 192, modes 10, 96x64"}
+    except Exception as exc:                                              # noqa: BLE001
+        out["config2_ufno_fno"] = {"error": repr(exc)[:200]}
+    torch.cuda.empty_cache()
+    if not args.no_scaled:
+        try:                                                              # config #5: scaled model + reduced precision report
+            from neural_pde_surrogates_b200 import _native
+            lib = _native.library()
+            wl5 = Workload(H=256, W=256, width=128, modes=32, blocks=6, name="cfg_twophase_ufno scaled")
+            Bs = 2
+            v32, ms32, p32, _ = train_rate(wl5, "UFNO", Bs, steps=2)
+            mode0 = lib.pdes_get_tensor_core_mode()
+            lib.pdes_set_tensor_core_mode(3)                               # single-pass TF32 in our GEMM kernels ...
+            try:
+                vtf, mstf, ptf, _ = train_rate(wl5, "UFNO", Bs, steps=2, tf32=True)   # ... and TF32 convs in cuDNN
+            finally:
+                lib.pdes_set_tensor_core_mode(mode0)
+                torch.backends.cudnn.allow_tf32 = args.tf32_convs
+            rel = float((ptf.double() - p32.double()).norm() / p32.double().norm())
+            out["config5_scaled"] = {"model": "U-FNO x6, width 128, modes 32x32, grid 256x256 (224 M parameters)", "per_gpu_batch": Bs,
+                                     "fp32": {"train_samples_per_s": v32, "ms_per_step": ms32},
+                                     "tf32": {"train_samples_per_s": vtf, "ms_per_step": mstf,
+                                              "forward_rel_l2_vs_fp32": rel, "stated_tolerance": 5e-3,
+                                              "what": "single-pass TF32 in the tcgen05 kernels + cuDNN TF32 convs; the "
+                                                      "reduced-precision mode is reported separately, never as the headline"}}
+            del p32, ptf
+        except Exception as exc:                                          # noqa: BLE001
+            out["config5_scaled"] = {"error": repr(exc)[:200]}
+        torch.cuda.empty_cache()
+    torch.backends.cudnn.allow_tf32 = args.tf32_convs
     return out
 
 
-def main():
+def run_legs(hx: Harness, args, wl: Workload = WL):
+    """All legs in a fixed order on every rank; returns the JSON line on rank 0 (None elsewhere)."""
+    t = leg_train(hx, args, wl)
+    extra = {}
+    if not args.no_extras:
+        extra["rollout"] = leg_rollout(hx, args, wl, t["trainer"], t["model"], t["pde"])
+        extra["train_unroll8"] = leg_unroll8(hx, args, wl, t["trainer"], t["pde"])
+        if hx.world == 1 and not args.no_other_configs:
+            extra.update(leg_other_configs(hx, args))
+    line = None
+    if hx.rank == 0:                                                       # collective-free from here on
+        B = args.batch
+        peak, peak_src = measured_peak()
+        chain = t["chain"]
+        fwd_us = statistics.mean(chain["block_forward"]) * 1e3 if chain["block_forward"] else None
+        bwd_us = statistics.mean(chain["block_backward"]) * 1e3 if chain["block_backward"] else None
+        ach = wl.block_bytes(B) / (fwd_us * 1e-6) / 1e9 if fwd_us else None
+        traffic, traffic_src = recorded_traffic(B)
+        cpu = None
+        if not args.no_extras and not args.no_cpu_baseline:
+            cpu = cpu_baseline_sample(B, wl)
+        line = {"metric": "train_samples_per_s", "value": t["value"], "unit": "samples/s", "n_gpus": hx.world,
+                "steps": args.steps, "warmup": t["warmup"], "ms_per_step": t["ms"] / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": workload_config(B, hx.world, wl),
+                "e2e": {"value": t["e2e_value"], "unit": "samples/s", "h2d_bytes_per_step": t["h2d"], "d2h_bytes_per_step": 4,
+                        "ms_per_step": t["ms_e2e"] / args.steps},
+                "gpu_launches": t["launches"], "clocks": t["clocks"],
+                "roofline": {"bound": "hbm", "kernel": "fno_block_forward chain (pruned forward DFT + per-mode channel mix + "
+                                                       "pruned inverse DFT fused with the 1x1 conv / bias / U-Net residual / GELU on tcgen05)",
+                             "achieved": ach, "peak": peak, "unit": "GB/s", "frac": (ach / peak) if ach else None,
+                             "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                             "alg_bytes_per_launch": wl.block_bytes(B), "us_per_launch": fwd_us,
+                             "launches_timed": len(chain["block_forward"]), "block_backward_us": bwd_us},
+                "cpu_baseline": cpu}
+        line.update(extra)
+    return line
+
+
+def run_ours(args):
+    hx = Harness()
+    if hx.world != args.gpus and hx.rank == 0:
+        print(f"warning: --gpus {args.gpus} but WORLD_SIZE={hx.world}", file=sys.stderr)
+    torch.backends.cudnn.allow_tf32 = args.tf32_convs
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.benchmark = not args.no_cudnn_benchmark
+    line = run_legs(hx, args)
+    if line is not None:
+        print(json.dumps(line), flush=True)
+    hx.finish()
+
+
+def make_parser():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=16, help="per-GPU batch (config default, defaults/base.py:6)")
-    ap.add_argument("--rollout-batch", type=int, default=16)
+    ap.add_argument("--rollout-batch", type=int, default=16, help="trajectories per GPU in the rollout leg")
+    ap.add_argument("--rollout-steps", type=int, default=50)
+    ap.add_argument("--unroll", type=int, default=8)
     ap.add_argument("--tf32-convs", action="store_true", help="let cuDNN use TF32 in the U-Net branch (reported separately)")
     ap.add_argument("--no-cudnn-benchmark", action="store_true",
                     help="do not let cuDNN autotune the conv algorithms of the U-Net branch (default: autotune on)")
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    args = ap.parse_args()
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the config #2 / #5 secondary numbers")
+    ap.add_argument("--no-scaled", action="store_true", help="skip config #5 (256x256, width 128, modes 32, 6 blocks)")
+    return ap
+
+
+def main():
+    args = make_parser().parse_args()
     if args.impl == "reference":
         run_reference(args)
     else:

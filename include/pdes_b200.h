@@ -100,6 +100,9 @@ int pdes_gemm_tc_supported(int N, int K);
 int pdes_inv_w_gemm_tc_ok(int N, int K, int H, int W, int m2, const float* x0, const float* x1);
 size_t pdes_gemm_tc_pack_floats(int K, int N);
 int pdes_gemm_tc_pack(const float* Wt, int lda, int K, int N, float* packed, void* stream);
+/* the same operand from the transposed storage W[n][k] (row stride ldw): an nn.Conv2d(k=1) weight [Cout][Cin]
+ * (proc_fno.py:114-117) feeds the forward GEMM directly, no transpose pass */
+int pdes_gemm_tc_pack_t(const float* W, int ldw, int K, int N, float* packed, void* stream);
 int pdes_inv_w_gemm_tc(const float* Z, const float* wpack, const float* x0, int C0, const float* x1, int C1,
                        const float* bias, const float* res, const float* tables, int backward_scale,
                        float* out, float* pre, int B, int N, int H, int W, int m1, int m2, int act, void* stream);
@@ -175,21 +178,23 @@ int pdes_gn_act_backward(const float* dy, const float* x, const float* gamma, co
 
 /* ---- fused chains (what the nn.Module binding calls) ----------------------------------------------------
  * One FNO_Layer / U-FNO block tail, forward:  K1 -> K2 -> K3a -> K3b.
- *   h [B,C0,H,W], vb [B,C1,H,W] or NULL, w1/w2 complex [Cin][Cout][m1][m2], wct [Cin][Cout] (NULL = no 1x1),
- *   bias [Cout] or NULL, res [B,Cout,H,W] or NULL (the U-Net branch), out [B,Cout,H,W],
- *   pre (NULL unless the backward will need it), Xsave [B][Cin][2MM] complex (kept for the backward),
- *   ws: pdes_block_fwd_workspace_floats() floats. */
+ *   h [B,C0,H,W], vb [B,C1,H,W] or NULL, w1/w2 complex [Cin][Cout][m1][m2], wc [Cout][Cin] = w.weight in its
+ *   parameter layout (NULL = no 1x1), wpack = pdes_gemm_tc_pack_t(wc, Cin, Cin, Cout) cached by the caller per weight
+ *   version or NULL (then it is packed into the workspace on every call), bias [Cout] or NULL, res [B,Cout,H,W] or
+ *   NULL (the U-Net branch), out [B,Cout,H,W], pre (NULL unless the backward will need it), Xsave [B][Cin][2MM]
+ *   complex (kept for the backward), ws: pdes_block_fwd_workspace_floats() floats. */
 size_t pdes_block_fwd_workspace_floats(int B, int Cin, int Cout, int H, int W, int m1, int m2);
 int pdes_block_forward(const float* h, int C0, const float* vb, int C1, const float* w1, const float* w2,
-                       const float* wct, const float* bias, const float* res, const float* tables,
-                       float* Xsave, float* ws, float* out, float* pre,
+                       const float* wc, const float* wpack, const float* bias, const float* res,
+                       const float* tables, float* Xsave, float* ws, float* out, float* pre,
                        int B, int Cout, int H, int W, int m1, int m2, int act, void* stream);
-/* backward of the same block.  Inputs: g_out, pre (if act != none), h, vb, Xsave, w1, w2, wc [Cout][Cin].
+/* backward of the same block.  Inputs: g_out, pre (if act != none), h, vb, Xsave, w1, w2, wc [Cout][Cin],
+ * wpack = pdes_gemm_tc_pack(wc, Cin, Cout, C0) or NULL.
  * Outputs: g_pre [B,Cout,H,W] (also the gradient of `res`), dh [B,C0,H,W], gw1/gw2 (parameter layout),
  * dwc [Cout][Cin] and dbias [Cout] (both may be NULL when there is no 1x1 conv). */
 size_t pdes_block_bwd_workspace_floats(int B, int C0, int C1, int Cout, int H, int W, int m1, int m2);
 int pdes_block_backward(const float* g_out, const float* pre, const float* h, int C0, const float* vb, int C1,
-                        const float* Xsave, const float* w1, const float* w2, const float* wc,
+                        const float* Xsave, const float* w1, const float* w2, const float* wc, const float* wpack,
                         const float* tables, float* ws, float* g_pre, float* dh, float* gw1, float* gw2,
                         float* dwc, float* dbias,
                         int B, int Cout, int H, int W, int m1, int m2, int act, void* stream);

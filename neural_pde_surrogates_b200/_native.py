@@ -39,6 +39,7 @@ _PROTOTYPES = {
     "pdes_inv_w_gemm_tc_ok": (c_int, [_I, _I, _I, _I, _I, _P, _P]),
     "pdes_gemm_tc_pack_floats": (c_size_t, [_I, _I]),
     "pdes_gemm_tc_pack": (c_int, [_P, _I, _I, _I, _P, _P]),
+    "pdes_gemm_tc_pack_t": (c_int, [_P, _I, _I, _I, _P, _P]),
     "pdes_inv_w_gemm_tc": (c_int, [_P, _P, _P, _I, _P, _I, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "pdes_wgrad_tc_workspace_floats": (c_size_t, [_I, _I]),
     "pdes_wgrad_tc": (c_int, [_P, _P, _I, _P, _I, _P, _P, _P, _I, _I, _I, _P]),
@@ -60,10 +61,10 @@ _PROTOTYPES = {
     "pdes_gn_act_forward": (c_int, [_P, _P, _P, ctypes.c_float, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "pdes_gn_act_backward": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "pdes_block_fwd_workspace_floats": (c_size_t, [_I, _I, _I, _I, _I, _I, _I]),
-    "pdes_block_forward": (c_int, [_P, _I, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
+    "pdes_block_forward": (c_int, [_P, _I, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                                    _I, _I, _I, _I, _I, _I, _I, _P]),
     "pdes_block_bwd_workspace_floats": (c_size_t, [_I, _I, _I, _I, _I, _I, _I, _I]),
-    "pdes_block_backward": (c_int, [_P, _P, _P, _I, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
+    "pdes_block_backward": (c_int, [_P, _P, _P, _I, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                                     _I, _I, _I, _I, _I, _I, _I, _P]),
 }
 

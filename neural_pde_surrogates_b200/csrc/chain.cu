@@ -6,7 +6,7 @@
 namespace pdes {
 namespace {
 
-struct FwdWs { size_t P, Z, PK, total; int nsplit; };
+struct FwdWs { size_t P, Z, PK, WT, total; int nsplit; };
 FwdWs fwd_ws(int B, int Cin, int Cout, int H, int W, int m1, int m2) {
   (void)W;
   FwdWs w;
@@ -15,7 +15,8 @@ FwdWs fwd_ws(int B, int Cin, int Cout, int H, int W, int m1, int m2) {
   w.P = 0;
   w.Z = w.P + round4((size_t)w.nsplit * B * Cout * M2 * 2);
   w.PK = w.Z + round4((size_t)B * H * 2 * m2 * Cout);
-  w.total = w.PK + round4(pdes_gemm_tc_pack_floats(Cin, Cout));      // packed 1x1 weights (tensor-core mode)
+  w.WT = w.PK + round4(pdes_gemm_tc_pack_floats(Cin, Cout));         // packed 1x1 weights (tensor-core mode)
+  w.total = w.WT + round4((size_t)Cin * Cout);                         // transposed 1x1 weights (FFMA mode)
   return w;
 }
 
@@ -46,11 +47,12 @@ size_t pdes_block_fwd_workspace_floats(int B, int Cin, int Cout, int H, int W, i
 }
 
 int pdes_block_forward(const float* h, int C0, const float* vb, int C1, const float* w1, const float* w2,
-                       const float* wct, const float* bias, const float* res, const float* tables, float* Xsave,
-                       float* ws, float* out, float* pre, int B, int Cout, int H, int W, int m1, int m2, int act,
-                       void* stream) {
+                       const float* wc, const float* wpack, const float* bias, const float* res, const float* tables,
+                       float* Xsave, float* ws, float* out, float* pre, int B, int Cout, int H, int W, int m1, int m2,
+                       int act, void* stream) {
   using namespace pdes;
   PDES_REQUIRE(h && w1 && w2 && tables && Xsave && ws && out, PDES_ERR_ARG, "pdes_block_forward: null pointer");
+  PDES_REQUIRE(wpack == nullptr || wc != nullptr, PDES_ERR_ARG, "pdes_block_forward: wpack without wc");
   const int Cin = C0 + C1;
   const FwdWs w = fwd_ws(B, Cin, Cout, H, W, m1, m2);
   float* P = ws + w.P;
@@ -58,10 +60,18 @@ int pdes_block_forward(const float* h, int C0, const float* vb, int C1, const fl
   if (int e = pdes_dft_fwd(h, C0, vb, C1, B, H, W, m1, m2, tables, 0, Xsave, stream)) return e;
   if (int e = pdes_mix_fwd(Xsave, w1, w2, P, w.nsplit, B, Cin, Cout, H, m1, m2, stream)) return e;
   if (int e = pdes_inv_h(P, w.nsplit, B, Cout, H, m1, m2, tables, Z, stream)) return e;
-  if (wct != nullptr && pdes_get_tensor_core_mode() && pdes_inv_w_gemm_tc_ok(Cout, Cin, H, W, m2, h, vb)) {
-    float* PK = ws + w.PK;
-    if (int e = pdes_gemm_tc_pack(wct, Cout, Cin, Cout, PK, stream)) return e;
+  if (wc != nullptr && pdes_get_tensor_core_mode() && pdes_inv_w_gemm_tc_ok(Cout, Cin, H, W, m2, h, vb)) {
+    const float* PK = wpack;
+    if (PK == nullptr) {                       // no cached operand: pack wc[o][i] as At[k = i][n = o] on the fly
+      if (int e = pdes_gemm_tc_pack_t(wc, Cin, Cin, Cout, ws + w.PK, stream)) return e;
+      PK = ws + w.PK;
+    }
     return pdes_inv_w_gemm_tc(Z, PK, h, C0, vb, C1, bias, res, tables, 0, out, pre, B, Cout, H, W, m1, m2, act, stream);
+  }
+  const float* wct = nullptr;
+  if (wc != nullptr) {                         // FFMA kernel reads At[i][o]
+    if (int e = pdes_transpose(wc, ws + w.WT, Cout, Cin, stream)) return e;
+    wct = ws + w.WT;
   }
   return pdes_inv_w_gemm(Z, wct, Cout, h, C0, vb, C1, bias, res, tables, 0, out, pre, B, Cout, H, W, m1, m2, act,
                          stream);
@@ -73,9 +83,9 @@ size_t pdes_block_bwd_workspace_floats(int B, int C0, int C1, int Cout, int H, i
 }
 
 int pdes_block_backward(const float* g_out, const float* pre, const float* h, int C0, const float* vb, int C1,
-                        const float* Xsave, const float* w1, const float* w2, const float* wc, const float* tables,
-                        float* ws, float* g_pre, float* dh, float* gw1, float* gw2, float* dwc, float* dbias, int B,
-                        int Cout, int H, int W, int m1, int m2, int act, void* stream) {
+                        const float* Xsave, const float* w1, const float* w2, const float* wc, const float* wpack,
+                        const float* tables, float* ws, float* g_pre, float* dh, float* gw1, float* gw2, float* dwc,
+                        float* dbias, int B, int Cout, int H, int W, int m1, int m2, int act, void* stream) {
   using namespace pdes;
   PDES_REQUIRE(g_out && h && Xsave && w1 && w2 && tables && ws && dh && gw1 && gw2, PDES_ERR_ARG,
                "pdes_block_backward: null pointer");
@@ -102,8 +112,11 @@ int pdes_block_backward(const float* g_out, const float* pre, const float* h, in
   // dh = Re(pruned inverse of GX, unit weights) + wc^T g_pre      (adjoint of K1 fused with the 1x1 dX)
   if (int e = pdes_inv_h(PX, w.nsplit, B, C0, H, m1, m2, tables, Zg, stream)) return e;
   if (has_conv && pdes_get_tensor_core_mode() && pdes_inv_w_gemm_tc_ok(C0, Cout, H, W, m2, gp, nullptr)) {
-    float* PK = ws + w.PK;                     // At[k = o][n = i] = wc[o][i], lda = Cin
-    if (int e = pdes_gemm_tc_pack(wc, Cin, Cout, C0, PK, stream)) return e;
+    const float* PK = wpack;                   // At[k = o][n = i] = wc[o][i], lda = Cin
+    if (PK == nullptr) {
+      if (int e = pdes_gemm_tc_pack(wc, Cin, Cout, C0, ws + w.PK, stream)) return e;
+      PK = ws + w.PK;
+    }
     if (int e = pdes_inv_w_gemm_tc(Zg, PK, gp, Cout, nullptr, 0, nullptr, nullptr, tables, 1, dh, nullptr, B, C0, H, W,
                                    m1, m2, PDES_ACT_NONE, stream))
       return e;

@@ -44,9 +44,9 @@ namespace {
 
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
 
-// Wt[k][n] (row stride lda) -> packed[chunk][hi|lo][canonical K-major block of N_pad rows x 16 k]
+// W(k, n) = Wt[k * sk + n * sn] -> packed[chunk][hi|lo][canonical K-major block of N_pad rows x 16 k]
 __global__ void __launch_bounds__(256)
-k_pack_b_tf32(const float* __restrict__ Wt, int lda, int K, int N, int npad, int nchunks, float* __restrict__ out) {
+k_pack_b_tf32(const float* __restrict__ Wt, size_t sk, size_t sn, int K, int N, int npad, int nchunks, float* __restrict__ out) {
   const int total = nchunks * npad * kTcBK;
   const int lbo_f = (npad / 8) * 32;                        // floats between K-adjacent core matrices
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
@@ -54,7 +54,7 @@ k_pack_b_tf32(const float* __restrict__ Wt, int lda, int K, int N, int npad, int
     const int kk = (idx / npad) % kTcBK;
     const int c = idx / (npad * kTcBK);
     const int k = c * kTcBK + kk;
-    const float w = (k < K && n < N) ? __ldg(Wt + (size_t)k * lda + n) : 0.0f;
+    const float w = (k < K && n < N) ? __ldg(Wt + (size_t)k * sk + (size_t)n * sn) : 0.0f;
     const float hi = tf32_hi(w);
     const size_t blk = (size_t)npad * kTcBK;
     const size_t off = (size_t)(kk / 4) * lbo_f + (size_t)(n / 8) * 32 + (n % 8) * 4 + (kk % 4);
@@ -1434,15 +1434,28 @@ size_t pdes_gemm_tc_pack_floats(int K, int N) {
   return (size_t)pdes::tc_nchunks(K) * 2 * pdes::tc_block_floats(N);
 }
 
-int pdes_gemm_tc_pack(const float* Wt, int lda, int K, int N, float* packed, void* stream) {
+static int gemm_tc_pack_impl(const float* Wt, size_t sk, size_t sn, int K, int N, float* packed, void* stream) {
   using namespace pdes;
-  PDES_REQUIRE(Wt && packed && K > 0 && N > 0 && lda >= N, PDES_ERR_ARG, "pdes_gemm_tc_pack: bad arguments");
   PDES_REQUIRE(pdes_gemm_tc_supported(N, K), PDES_ERR_UNSUPPORTED, "pdes_gemm_tc_pack: N=%d > %d", N, kTcMaxN);
   const int npad = tc_npad(N), nchunks = tc_nchunks(K);
   const int total = nchunks * npad * kTcBK;
   auto kfn = k_pack_b_tf32;
-  PDES_LAUNCH(kfn, dim3((unsigned)ceil_div(total, 256)), dim3(256), 0, stream, Wt, lda, K, N, npad, nchunks, packed);
+  PDES_LAUNCH(kfn, dim3((unsigned)ceil_div(total, 256)), dim3(256), 0, stream, Wt, sk, sn, K, N, npad, nchunks, packed);
   return check_launch("pdes_gemm_tc_pack");
+}
+
+int pdes_gemm_tc_pack(const float* Wt, int lda, int K, int N, float* packed, void* stream) {
+  using namespace pdes;
+  PDES_REQUIRE(Wt && packed && K > 0 && N > 0 && lda >= N, PDES_ERR_ARG, "pdes_gemm_tc_pack: bad arguments");
+  return gemm_tc_pack_impl(Wt, (size_t)lda, 1, K, N, packed, stream);
+}
+
+/* Same packed operand from the transposed storage W[n][k] (row stride ldw >= K): this is how an nn.Conv2d(k=1) weight
+ * [Cout][Cin] feeds the forward GEMM (K = Cin, N = Cout) without a separate transpose pass. */
+int pdes_gemm_tc_pack_t(const float* W, int ldw, int K, int N, float* packed, void* stream) {
+  using namespace pdes;
+  PDES_REQUIRE(W && packed && K > 0 && N > 0 && ldw >= K, PDES_ERR_ARG, "pdes_gemm_tc_pack_t: bad arguments");
+  return gemm_tc_pack_impl(W, 1, (size_t)ldw, K, N, packed, stream);
 }
 
 }  // extern "C"

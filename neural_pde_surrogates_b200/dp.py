@@ -83,6 +83,8 @@ def make_data_parallel(trainer, seed: int = 42):
         for p in trainer.model.parameters():                       # identical replicas
             t = torch.view_as_real(p.data) if p.is_complex() else p.data
             dist.broadcast(t, src=0)
+        from . import ops                                           # `.data` writes do not bump Parameter._version
+        ops.invalidate_weight_caches()
     bucket = GradBucket(trainer.model.parameters())
     trainer.rng_unroll = random.Random(seed)                       # same on every rank
     trainer.rng_steps = random.Random(seed * 7919 + 1 + rank)      # different per rank

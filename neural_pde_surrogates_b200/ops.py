@@ -10,6 +10,8 @@ bookkeeping only; every arithmetic pass over the data is a kernel from csrc/.
 """
 from __future__ import annotations
 
+import weakref
+
 import numpy as np
 import torch
 
@@ -18,7 +20,44 @@ from . import _native
 ACT_NONE, ACT_GELU = _native.ACT_NONE, _native.ACT_GELU
 
 _tables_cache: dict = {}
-_wct_cache: dict = {}
+
+
+class _PackCache:
+    """Tensor-core operands (hi/lo TF32 split, UMMA canonical layout) packed from a weight, reused until the weight
+    changes.  Keyed by the Parameter OBJECT through a weak reference (never by address alone: the caching allocator
+    hands a freed model's addresses to the next one) and validated by `_version`, `data_ptr`, shape and a global epoch.
+    In-place updates (optimizer steps, `load_state_dict`, `copy_`) bump `_version`; writes that bypass the version
+    counter (`p.data.copy_()`, `dist.broadcast(p.data)`) must be followed by `invalidate_weight_caches()` -- dp.py
+    does so.  During CUDA-graph capture the cache is bypassed (the pack kernel is captured with the graph), so a
+    replay always sees the current weights."""
+
+    def __init__(self):
+        self._d = {}
+        self.epoch = 0
+
+    def get(self, param, kind, build):
+        if param is None or torch.cuda.is_current_stream_capturing():
+            return None
+        key = id(param)
+        stamp = (param._version, param.data_ptr(), tuple(param.shape), self.epoch)
+        ent = self._d.get(key)
+        if ent is None or ent[0]() is not param or ent[1] != stamp:
+            ent = (weakref.ref(param, lambda _r, k=key, d=self._d: d.pop(k, None)), stamp, {})
+            self._d[key] = ent
+        t = ent[2].get(kind)
+        if t is None:
+            t = build()
+            ent[2][kind] = t
+        return t
+
+
+_pack_cache = _PackCache()
+
+
+def invalidate_weight_caches():
+    """Forget every packed weight operand (call after writing parameters through `.data` or a raw pointer)."""
+    _pack_cache.epoch += 1
+    _pack_cache._d.clear()
 
 # ---- instrumentation used by bench.py: kernel-launch counter and in-situ CUDA-event timing of the two chains
 _counters = {"launches": 0}
@@ -41,7 +80,8 @@ def enable_timing(flag: bool):
 
 def collect_timings():
     """Milliseconds per recorded chain launch (synchronises)."""
-    torch.cuda.synchronize()
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
     return {k: [a.elapsed_time(b) for a, b in _timing[k]] for k in ("block_forward", "block_backward")}
 
 
@@ -86,20 +126,28 @@ def tables_for(device: torch.device, H: int, W: int, m1: int, m2: int) -> torch.
     return t
 
 
-def _transposed_conv_weight(wc: torch.Tensor) -> torch.Tensor:
-    """[Cout, Cin(,1,1)] -> [Cin, Cout] with our own transpose kernel; cached until the parameter changes."""
-    Cout, Cin = wc.shape[0], wc.shape[1]
-    key = (wc.data_ptr(), wc.device.index)
-    hit = _wct_cache.get(key)
-    if hit is not None and hit[0] == wc._version and hit[1].shape == (Cin, Cout) and not torch.cuda.is_current_stream_capturing():
-        return hit[1]
-    wct = torch.empty(Cin, Cout, device=wc.device, dtype=torch.float32)
+def _pack_1x1(weight, K, N, transposed: bool, col_off: int = 0):
+    """pdes_gemm_tc_pack(_t) of a 1x1-conv weight [Cout][Cin(,1,1)] into a fresh buffer.
+    transposed=True : operand At[k = i][n = o] = w[o][i]                       (forward GEMM, K = Cin, N = Cout)
+    transposed=False: operand At[k = o][n = i] = w[o][col_off + i], i < N      (input-gradient GEMM, K = Cout)"""
     lib = _lib()
-    _native.check(lib, lib.pdes_transpose(wc.data_ptr(), wct.data_ptr(), Cout, Cin, _stream()))
+    Cout = weight.shape[0]
+    w2 = weight.detach().reshape(Cout, -1)
+    if not w2.is_contiguous():
+        w2 = w2.contiguous()
+    Cin = w2.shape[1]
+    pack = torch.empty(lib.pdes_gemm_tc_pack_floats(K, N), dtype=torch.float32, device=weight.device)
+    if transposed:
+        _native.check(lib, lib.pdes_gemm_tc_pack_t(w2.data_ptr(), Cin, K, N, pack.data_ptr(), _stream()))
+    else:
+        _native.check(lib, lib.pdes_gemm_tc_pack(w2.data_ptr() + 4 * col_off, Cin, K, N, pack.data_ptr(), _stream()))
     _counters["launches"] += 1
-    if not torch.cuda.is_current_stream_capturing():
-        _wct_cache[key] = (wc._version, wct)
-    return wct
+    return pack
+
+
+def _tc_pack_usable(weight) -> bool:
+    return (weight is not None and weight.is_cuda and weight.dtype == torch.float32
+            and _lib().pdes_get_tensor_core_mode() >= 1)
 
 
 def _check_f32_cuda(name, t, ndim=None):
@@ -115,7 +163,7 @@ def _check_f32_cuda(name, t, ndim=None):
 
 class FNOBlockFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, h, vb, res, w1, w2, wc, bias, act):
+    def forward(ctx, h, vb, res, w1, w2, wc, bias, act, wpack_f=None, wpack_b=None):
         lib = _lib()
         _check_f32_cuda("h", h, 4)
         _check_f32_cuda("variables_broadcast", vb, 4)
@@ -137,15 +185,16 @@ class FNOBlockFunction(torch.autograd.Function):
         res = None if res is None else res.contiguous()
         w1c, w2c = w1.contiguous(), w2.contiguous()
         dev = h.device
-        needs_grad = any(ctx.needs_input_grad)
+        # needs_input_grad ignores grad mode: under torch.no_grad() (rollout, push-forward unroll) nothing is saved
+        # and K3b does not store the pre-activation
+        needs_grad = torch.is_grad_enabled() and any(ctx.needs_input_grad)
         with torch.cuda.device(dev):
             tab = tables_for(dev, H, W, m1, m2)
-            wct = None
+            wc2 = None
             if wc is not None:
                 wc2 = wc.reshape(Cout, Cin)
                 if not wc2.is_contiguous():
                     wc2 = wc2.contiguous()
-                wct = _transposed_conv_weight(wc2)
             X = torch.empty(B, Cin, 2 * m1, m2, dtype=torch.complex64, device=dev)
             out = torch.empty(B, Cout, H, W, dtype=torch.float32, device=dev)
             pre = torch.empty_like(out) if (needs_grad and act != ACT_NONE) else None
@@ -153,11 +202,11 @@ class FNOBlockFunction(torch.autograd.Function):
             p = lambda t: None if t is None else t.data_ptr()
             with _Timed("block_forward"):
                 _native.check(lib, lib.pdes_block_forward(
-                    p(h), C0, p(vb), C1, p(w1c), p(w2c), p(wct), p(bias), p(res), p(tab), p(X), p(ws), p(out), p(pre),
-                    B, Cout, H, W, m1, m2, act, _stream()))
-            _counters["launches"] += 4          # K1, K2, K3a, K3b
+                    p(h), C0, p(vb), C1, p(w1c), p(w2c), p(wc2), p(wpack_f), p(bias), p(res), p(tab), p(X), p(ws), p(out),
+                    p(pre), B, Cout, H, W, m1, m2, act, _stream()))
+            _counters["launches"] += 4 + (1 if (wc is not None and wpack_f is None) else 0)   # K1, K2, K3a, K3b (+ pack)
         if needs_grad:
-            ctx.save_for_backward(h, vb, w1c, w2c, wc, X, pre)
+            ctx.save_for_backward(h, vb, w1c, w2c, wc, X, pre, wpack_b)
             ctx.act = act
             ctx.has_res = res is not None
             ctx.has_bias = bias is not None
@@ -166,7 +215,7 @@ class FNOBlockFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         lib = _lib()
-        h, vb, w1, w2, wc, X, pre = ctx.saved_tensors
+        h, vb, w1, w2, wc, X, pre, wpack_b = ctx.saved_tensors
         if ctx.needs_input_grad[1]:
             raise NotImplementedError("gradient w.r.t. the broadcast conditioning channels is not implemented "
                                       "(they never require grad in the twophase configs, enc_proc_dec.py:126-137)")
@@ -192,17 +241,24 @@ class FNOBlockFunction(torch.autograd.Function):
             p = lambda t: None if t is None else t.data_ptr()
             with _Timed("block_backward"):
                 _native.check(lib, lib.pdes_block_backward(
-                    p(g), p(pre), p(h), C0, p(vb), C1, p(X), p(w1), p(w2), p(wc2), p(tab), p(ws), p(g_pre), p(dh),
+                    p(g), p(pre), p(h), C0, p(vb), C1, p(X), p(w1), p(w2), p(wc2), p(wpack_b), p(tab), p(ws), p(g_pre), p(dh),
                     p(gw1), p(gw2), p(dwc), p(dbias), B, Cout, H, W, m1, m2, act, _stream()))
             # act_bwd, K1(g), mix_dw, mix_dx, K3a, K3b, wgrad + its reduce
-            _counters["launches"] += 5 + (1 if act != ACT_NONE else 0) + (2 if wc is not None else 0)
+            _counters["launches"] += 5 + (1 if act != ACT_NONE else 0) + (2 if wc is not None else 0) + \
+                (1 if (wc is not None and wpack_b is None) else 0)
         d_res = (g_pre if act != ACT_NONE else g) if ctx.has_res else None
-        return dh, None, d_res, gw1, gw2, (None if dwc is None else dwc.view_as(wc)), dbias, None
+        return dh, None, d_res, gw1, gw2, (None if dwc is None else dwc.view_as(wc)), dbias, None, None, None
 
 
 def fno_block(h, vb, res, w1, w2, wc, bias, act: int = ACT_NONE):
     """act(spectral(cat[h,vb]) + conv1x1(cat[h,vb]) + bias + res); any of vb / res / wc / bias may be None."""
-    return FNOBlockFunction.apply(h, vb, res, w1, w2, wc, bias, act)
+    wpack_f = wpack_b = None
+    if wc is not None and _tc_pack_usable(wc):
+        Cout, Cin, C0 = wc.shape[0], w1.shape[0], h.shape[1]
+        wpack_f = _pack_cache.get(wc, ("f", Cin, Cout), lambda: _pack_1x1(wc, Cin, Cout, True))
+        if torch.is_grad_enabled() and (h.requires_grad or wc.requires_grad or w1.requires_grad):
+            wpack_b = _pack_cache.get(wc, ("b", Cout, C0, 0), lambda: _pack_1x1(wc, Cout, C0, False))
+    return FNOBlockFunction.apply(h, vb, res, w1, w2, wc, bias, act, wpack_f, wpack_b)
 
 
 def act_code(module) -> int | None:
@@ -235,8 +291,9 @@ class GroupNormActFunction(torch.autograd.Function):
             _native.check(lib, lib.pdes_gn_act_forward(p(x), p(weight), p(bias), float(eps), p(y), p(stats), p(ws),
                                                        B, C, HW, groups, act, _stream()))
             _counters["launches"] += 3
-        ctx.save_for_backward(x, weight, bias, stats)
-        ctx.groups, ctx.act = groups, act
+        if torch.is_grad_enabled():
+            ctx.save_for_backward(x, weight, bias, stats)
+            ctx.groups, ctx.act = groups, act
         return y
 
     @staticmethod
@@ -382,15 +439,16 @@ class Conv1x1Function(torch.autograd.Function):
         dev = x.device
         p = lambda t: None if t is None else t.data_ptr()
         with torch.cuda.device(dev):
-            wt = weight.detach().reshape(N, Cin).t().contiguous()                  # [Cin][N]
-            pack = torch.empty(lib.pdes_gemm_tc_pack_floats(Cin, N), dtype=torch.float32, device=dev)
+            pack = _pack_cache.get(weight, ("f", Cin, N), lambda: _pack_1x1(weight, Cin, N, True))
+            if pack is None:                                                        # graph capture: pack in-graph
+                pack = _pack_1x1(weight, Cin, N, True)
             out = torch.empty(B, N, H, W, dtype=torch.float32, device=dev)
             st = _stream()
-            _native.check(lib, lib.pdes_gemm_tc_pack(p(wt), N, Cin, N, p(pack), st))
             _native.check(lib, lib.pdes_conv1x1_tc(p(x), Cin, p(pack), p(bias), None, p(out), N * HW, B, N, HW, ACT_NONE, st))
-            _counters["launches"] += 3
-        ctx.save_for_backward(x, weight)
-        ctx.has_bias = bias is not None
+            _counters["launches"] += 1
+        if torch.is_grad_enabled():
+            ctx.save_for_backward(x, weight)
+            ctx.has_bias = bias is not None
         return out
 
     @staticmethod
@@ -410,12 +468,13 @@ class Conv1x1Function(torch.autograd.Function):
                 w2 = w2.contiguous()
             if ctx.needs_input_grad[0]:
                 gx = torch.empty_like(x)
-                pack = torch.empty(lib.pdes_gemm_tc_pack_floats(N, min(Cin, _C1_MAX_N)), dtype=torch.float32, device=dev)
                 for off, n in _ranges(Cin, _C1_MAX_N):            # dx[:, off:off+n] = w[:, off:off+n]^T g
-                    _native.check(lib, lib.pdes_gemm_tc_pack(p(w2) + 4 * off, Cin, N, n, p(pack), st))
+                    pack = _pack_cache.get(weight, ("b", N, n, off), lambda: _pack_1x1(weight, N, n, False, off))
+                    if pack is None:
+                        pack = _pack_1x1(weight, N, n, False, off)
                     _native.check(lib, lib.pdes_conv1x1_tc(p(g), N, p(pack), None, None, p(gx) + 4 * off * HW, Cin * HW, B, n, HW,
                                                            ACT_NONE, st))
-                    _counters["launches"] += 2
+                    _counters["launches"] += 1
             if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
                 gw = torch.empty(N, Cin, dtype=torch.float32, device=dev)
                 gb = torch.empty(N, dtype=torch.float32, device=dev) if ctx.has_bias else None

@@ -60,11 +60,15 @@ def _process_step_identity(pde):
 
 
 class GraphedModelStep:
-    """One model application captured in a CUDA graph: out = model(u, cond, pos, spatial_cond) with static buffers."""
+    """One model application captured in a CUDA graph: out = model(u, cond, pos, spatial_cond).  Every input lives in a
+    static buffer owned by this object and is refreshed on each call, so a replay can never see stale conditioning."""
 
     def __init__(self, model, u, cond, pos, spatial_cond, warmup: int = 3):
-        self.u = u.clone()
-        self.kw = dict(cond=cond, bc=None, pos=pos, t_cond=None, spatial_cond=spatial_cond)
+        own = lambda t: None if t is None else t.detach().clone()
+        self.u = own(u)
+        self.static = dict(cond=own(cond), pos=own(pos), spatial_cond=own(spatial_cond))
+        self.kw = dict(cond=self.static["cond"], bc=None, pos=self.static["pos"], t_cond=None,
+                       spatial_cond=self.static["spatial_cond"])
         side = torch.cuda.Stream(device=u.device)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side), torch.no_grad():
@@ -75,7 +79,19 @@ class GraphedModelStep:
         with torch.cuda.graph(self.graph), torch.no_grad():
             self.out = model(self.u, **self.kw)
 
-    def __call__(self, u):
+    def signature(self, u, cond, pos, spatial_cond):
+        sig = lambda t: None if t is None else (tuple(t.shape), t.dtype, t.device)
+        return (sig(u), sig(cond), sig(pos), sig(spatial_cond))
+
+    def matches(self, u, cond, pos, spatial_cond) -> bool:
+        return self.signature(u, cond, pos, spatial_cond) == self.signature(self.u, *(self.static[k] for k in ("cond", "pos", "spatial_cond")))
+
+    def __call__(self, u, cond=None, pos=None, spatial_cond=None, refresh: bool = True):
+        if refresh:
+            for k, t in (("cond", cond), ("pos", pos), ("spatial_cond", spatial_cond)):
+                buf = self.static[k]
+                if buf is not None and t is not None and buf.numel() and t.data_ptr() != buf.data_ptr():
+                    buf.copy_(t)
         if u.data_ptr() != self.u.data_ptr():
             self.u.copy_(u)
         self.graph.replay()
@@ -160,11 +176,10 @@ class AutoregressivePushforwardTrainer:
             return self.model(pred, cond=conditioning, bc=None, pos=x, t_cond=None, spatial_cond=spatial_cond)
         key = (tuple(pred.shape), pred.device.index)
         g = self._graphs.get(key)
-        if g is None or g.kw["pos"].data_ptr() != x.data_ptr() or \
-                (spatial_cond is not None and g.kw["spatial_cond"].data_ptr() != spatial_cond.data_ptr()):
+        if g is None or not g.matches(pred, conditioning, x, spatial_cond):
             g = GraphedModelStep(self.model, pred, conditioning, x, spatial_cond)
             self._graphs[key] = g
-        return g(pred).clone()
+        return g(pred, conditioning, x, spatial_cond).clone()
 
     def simulate(self, u, conditioning, x, compute_loss, include_data, nr_gt_steps, t_res,
                  t_conditioning=torch.empty(0), spatial_conditioning=torch.empty(0), clip_min=True, use_bc=True,

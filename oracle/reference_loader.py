@@ -1,9 +1,11 @@
-"""Import the *unmodified* reference modules from /root/reference (TEST INFRASTRUCTURE ONLY).
+"""Import the *unmodified* reference modules (TEST INFRASTRUCTURE ONLY).
 
-Only usable in the build container: /root/reference does not exist on the GPU box, so nothing
-that runs there (`-m gpu` tests, `smoke()`, `bench.py`) may call this.  It is used by
-`tests/golden/make_golden.py` (fixture generator) and by the CPU tests that pin the oracle and
-the torch port against the real reference when it is present.
+Two locations, tried in this order:
+  1. /root/reference/src  -- the read-only mount of the build container (absent on the GPU box);
+  2. oracle/_ref/src      -- the verbatim copy made by `oracle/make_ref.sh` (git-ignored, travels to the GPU box).
+Used by `tests/golden/make_golden.py` (fixture generator), by the tests that pin the oracle / torch port / product
+modules against the real reference, and by the `cpu_baseline` / `--impl reference` legs of bench.py (which time the
+reference's own CPU implementation).  The product package never imports this file.
 
 Two import-only stubs are needed: `torch_geometric.data.Data` and
 `mmap_ninja.ragged.RaggedMmap`; neither symbol is touched on the grid path.
@@ -14,11 +16,29 @@ import os
 import sys
 import types
 
-REFERENCE_SRC = os.environ.get("PDES_REFERENCE_SRC", "/root/reference/src")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_CANDIDATES = [os.environ.get("PDES_REFERENCE_SRC"), "/root/reference/src", os.path.join(_HERE, "_ref", "src")]
+
+
+def _find_src():
+    for c in _CANDIDATES:
+        if c and os.path.isdir(os.path.join(c, "models")):
+            return c
+    return None
+
+
+REFERENCE_SRC = _find_src() or "/root/reference/src"
 
 
 def reference_available() -> bool:
     return os.path.isdir(os.path.join(REFERENCE_SRC, "models"))
+
+
+def reference_kind() -> str:
+    """'mount' (read-only /root/reference), 'vendored' (oracle/_ref copy) or 'absent'."""
+    if not reference_available():
+        return "absent"
+    return "vendored" if os.path.realpath(REFERENCE_SRC).startswith(os.path.realpath(_HERE)) else "mount"
 
 
 def load_reference():

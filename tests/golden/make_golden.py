@@ -115,12 +115,63 @@ def model_case(ref):
     np.savez_compressed(os.path.join(HERE, "model_tiny.npz"), **out)
 
 
+def trainer_case(ref):
+    """The reference trainer's own train_step with a non-zero push-forward unroll (epoch 50 => u in {0,1,2}, drawn from
+    the seeded global `random`, autoregressivepushforwardtrainer.py:78-95) + backward, and its test_step
+    (:165-286, incl. _test_unrolled_losses :442-514) on whole synthetic trajectories.  Model = model_tiny.npz's."""
+    import random
+    from types import SimpleNamespace
+    from common.data_creator import DataCreator
+    from common.interfaces import D
+    from neural_pde_surrogates_b200.shell import twophase_model_kwargs
+    H, W, B, T = 24, 16, 2, 150
+    pde = twophase_pde(ref, H, W)
+    torch.manual_seed(42)
+    kw = twophase_model_kwargs("UFNO", hidden_features=16, fno_modes=4, hidden_blocks=2)
+    model = ref.models.activation_wrapper(model_class="EncProcDec", **kw, pde=pde)      # same init as model_case
+    torch.manual_seed(5)
+    u_super = torch.rand(B, 1, T, H, W) * 0.5 + 0.1
+    mask = (torch.rand(B, 1, H, W) < 0.1).float()
+    pos = pde.x[None].repeat(B, 1, 1, 1)
+    batch = (torch.empty(0), u_super, pos, torch.empty(B, 0), torch.empty(0), mask)
+    Tr = ref.trainer.AutoregressivePushforwardTrainer
+    tr = Tr.__new__(Tr)
+    tr.config = SimpleNamespace(device="cpu", batch_size=B, lr_step_interval=25, unrolling=8, process_settings={},
+                                base_resolution=(T, H, W), time_window=25, nr_gt_steps=1)
+    tr.model, tr.criterion = model, torch.nn.MSELoss(reduction="sum")
+    tr.data = SimpleNamespace(pde=pde, data_interface=D.sim2d)
+    tr.data_creator = DataCreator(pde=pde, neighbors=3, time_window=25, t_resolution=T, x_resolution=H)
+    out = {"u_super": npy(u_super), "mask": npy(mask), "epoch": np.array(50)}
+    for seed in (3, 7, 5):                                    # seeds chosen to cover unroll counts 0, 1 and 2
+        random.seed(seed)
+        st = random.getstate()
+        unrolled = random.choice(list(range(3)))
+        random.setstate(st)
+        model.zero_grad()
+        loss, pred = tr.train_step(batch, 50, 0, None)
+        loss.backward()
+        out[f"ts{seed}_unrolled"] = np.array(unrolled)
+        out[f"ts{seed}_loss"] = npy(loss)
+        out[f"ts{seed}_pred"] = npy(pred)
+        for k, p in model.named_parameters():
+            if k.endswith("conv.weights1") or k.endswith("w.weight") or k.startswith("encoder.encoder.0.weight"):
+                out[f"ts{seed}_grad_{k}"] = npy(p.grad)
+    with torch.no_grad():
+        val, info = tr.test_step(batch, 0)
+    out["test_loss"] = npy(val)
+    for k, v in info.items():
+        out["test_info_" + k.replace(" ", "_").replace(",", "")] = npy(torch.as_tensor(v))
+    np.savez_compressed(os.path.join(HERE, "trainer_steps.npz"), **out)
+    print("trainer_case unroll counts:", {s: int(out[f"ts{s}_unrolled"]) for s in (3, 7, 5)})
+
+
 if __name__ == "__main__":
     torch.set_num_threads(4)
     ref = load_reference()
     spectral_cases(ref)
     block_case(ref)
     model_case(ref)
+    trainer_case(ref)
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")

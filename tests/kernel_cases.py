@@ -177,16 +177,12 @@ def run_block(be, shape, d, act=1, use_res=True, use_conv=True):
     lib = be.lib
     tab = be.tables(H, W, m1, m2)
     up = {k: (be.upload(v) if v is not None else None) for k, v in d.items()}
-    wct = None
-    if use_conv:
-        wct = be.empty((Cin, Cout))
-        be.check(lib.pdes_transpose(be.ptr(up["wc"]), be.ptr(wct), Cout, Cin, be.stream))
     X = be.empty((B, Cin, 2 * m1, m2), complex_=True)
     ws = be.empty((lib.pdes_block_fwd_workspace_floats(B, Cin, Cout, H, W, m1, m2),))
     out = be.empty((B, Cout, H, W))
     pre = be.empty((B, Cout, H, W))
     be.check(lib.pdes_block_forward(be.ptr(up["h"]), C0, be.ptr(up["vb"]), C1, be.ptr(up["w1"]), be.ptr(up["w2"]),
-                                    be.ptr(wct), be.ptr(up["bias"]) if use_conv else None,
+                                    be.ptr(up["wc"]) if use_conv else None, None, be.ptr(up["bias"]) if use_conv else None,
                                     be.ptr(up["res"]) if use_res else None, be.ptr(tab), be.ptr(X), be.ptr(ws),
                                     be.ptr(out), be.ptr(pre), B, Cout, H, W, m1, m2, act, be.stream))
     wsb = be.empty((lib.pdes_block_bwd_workspace_floats(B, C0, C1, Cout, H, W, m1, m2),))
@@ -198,7 +194,7 @@ def run_block(be, shape, d, act=1, use_res=True, use_conv=True):
     dbias = be.empty((Cout,))
     be.check(lib.pdes_block_backward(be.ptr(up["g"]), be.ptr(pre), be.ptr(up["h"]), C0, be.ptr(up["vb"]), C1,
                                      be.ptr(X), be.ptr(up["w1"]), be.ptr(up["w2"]),
-                                     be.ptr(up["wc"]) if use_conv else None, be.ptr(tab), be.ptr(wsb),
+                                     be.ptr(up["wc"]) if use_conv else None, None, be.ptr(tab), be.ptr(wsb),
                                      be.ptr(g_pre), be.ptr(dh), be.ptr(gw1), be.ptr(gw2),
                                      be.ptr(dwc) if use_conv else None, be.ptr(dbias) if use_conv else None,
                                      B, Cout, H, W, m1, m2, act, be.stream))

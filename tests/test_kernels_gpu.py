@@ -10,6 +10,7 @@ pytestmark = pytest.mark.gpu
 FULL_SHAPES = [
     (4, 192, 1, 192, 96, 64, 10, 10),
     (2, 128, 1, 128, 64, 64, 16, 16),
+    (16, 192, 1, 192, 96, 64, 10, 10),       # the bench batch at full channels (B > 8 tile configs of the mix kernels)
 ]
 
 

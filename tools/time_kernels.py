@@ -93,7 +93,7 @@ def main():
                                             ck(lib.pdes_inv_w_gemm_tc(p(Z), p(pack), p(h), C0, p(vb), C1, p(bias), p(res), p(tab), 0,
                                                                       p(outp), None, B, Cout, H, W, m1, m2, 1, st))),
                                    4 * B * Cin * HW + 8 * B * Cout * HW + 4 * B * H * 2 * m2 * Cout),
-            "block_forward": (lambda: ck(lib.pdes_block_forward(p(h), C0, p(vb), C1, p(w1), p(w2), p(wct), p(bias), p(res),
+            "block_forward": (lambda: ck(lib.pdes_block_forward(p(h), C0, p(vb), C1, p(w1), p(w2), p(wc), None, p(bias), p(res),
                                                                 p(tab), p(X), p(ws), p(outp), None, B, Cout, H, W, m1, m2, 1, st)),
                               4 * B * Cin * HW + 16 * Cin * Cout * MM + 8 * B * Cout * HW + 4 * Cout * Cin + 4 * Cout),
             "act_bwd": (lambda: ck(lib.pdes_act_bwd(p(g), p(pre), p(gpre), g.numel(), 1, st)), 12 * B * Cout * HW),
@@ -103,7 +103,7 @@ def main():
                       4 * B * (Cin + Cout) * HW),
             "wgrad_tcgen05": (lambda: ck(lib.pdes_wgrad_tc(p(g), p(h), C0, p(vb), C1, p(dwc), p(dbias), p(wgtc), B, Cout, HW, st)),
                               4 * B * (Cin + Cout) * HW),
-            "block_backward": (lambda: ck(lib.pdes_block_backward(p(g), p(pre), p(h), C0, p(vb), C1, p(X), p(w1), p(w2), p(wc),
+            "block_backward": (lambda: ck(lib.pdes_block_backward(p(g), p(pre), p(h), C0, p(vb), C1, p(X), p(w1), p(w2), p(wc), None,
                                                                   p(tab), p(wsb), p(gpre), p(dh), p(gw1), p(gw2), p(dwc), p(dbias),
                                                                   B, Cout, H, W, m1, m2, 1, st)),
                                4 * B * (3 * Cout + 2 * Cin + C0) * HW + 32 * Cin * Cout * MM),
