@@ -16,7 +16,7 @@ constexpr int kK1Threads = 128;
 __global__ void __launch_bounds__(kK1Threads)
 k_dft_fwd(const float* __restrict__ x0, int C0, const float* __restrict__ x1, int C1, int H, int W, int m1, int m2,
           int nc4, int R, int xs_stride, const float* __restrict__ twa_g, const float* __restrict__ twh_g,
-          const float* __restrict__ lscale, float* __restrict__ X) {
+          const float* __restrict__ lscale, float* __restrict__ X, float2* __restrict__ X2, int B, int CinP) {
   PDES_DYN_SMEM(float, smem);
   float* xs = smem;                                     // [R][xs_stride]
   float* twa = xs + round4((size_t)R * xs_stride);      // [W][nc4]
@@ -118,6 +118,7 @@ k_dft_fwd(const float* __restrict__ x0, int C0, const float* __restrict__ x1, in
     }
     float* o = X + ((size_t)img * nout + n) * 2;
     o[0] = ar; o[1] = ai;
+    if (X2 != nullptr) X2[((size_t)n * B + b) * CinP + c] = make_float2(ar, ai);      // mode-major copy for K2 on tcgen05
   }
 }
 
@@ -190,7 +191,8 @@ __device__ __forceinline__ void dft_fast_stage1(const float* __restrict__ col, f
 template <int H, int W, int M1, int M2>
 __global__ void __launch_bounds__(2 * W)
 k_dft_fwd_fast(const float* __restrict__ x0, int C0, const float* __restrict__ x1, int C1,
-               const float* __restrict__ twa_g, int nc4, const float* __restrict__ lscale, float* __restrict__ X) {
+               const float* __restrict__ twa_g, int nc4, const float* __restrict__ lscale, float* __restrict__ X,
+               float2* __restrict__ X2, int B, int CinP) {
   static_assert(H == 96, "twiddle table instantiated for H = 96");
   static_assert(H % 2 == 0 && 2 * M1 <= H && M2 <= W / 2 + 1, "fast path preconditions");
   constexpr int NK = M1 + 1;                 // |kx| = 0 .. M1
@@ -254,13 +256,17 @@ k_dft_fwd_fast(const float* __restrict__ x0, int C0, const float* __restrict__ x
     const float sc = (lscale != nullptr) ? __ldg(lscale + l) : 1.0f;
     if (kxi < M1) {                          // +kx -> row k = kx:  sum (P - iQ)(c - is)
       float* o = Xo + ((size_t)kxi * M2 + l) * 2;
-      o[0] = sc * (a - d);
-      o[1] = -sc * (bs + cq);
+      const float vr = sc * (a - d), vi = -sc * (bs + cq);
+      o[0] = vr;
+      o[1] = vi;
+      if (X2 != nullptr) X2[((size_t)(kxi * M2 + l) * B + b) * CinP + c] = make_float2(vr, vi);
     }
     if (kxi > 0) {                           // -kx -> row k = 2*M1 - kx:  sum (P + iQ)(c - is)
       float* o = Xo + ((size_t)(2 * M1 - kxi) * M2 + l) * 2;
-      o[0] = sc * (a + d);
-      o[1] = sc * (cq - bs);
+      const float vr = sc * (a + d), vi = sc * (cq - bs);
+      o[0] = vr;
+      o[1] = vi;
+      if (X2 != nullptr) X2[((size_t)((2 * M1 - kxi) * M2 + l) * B + b) * CinP + c] = make_float2(vr, vi);
     }
   }
 }
@@ -268,9 +274,11 @@ k_dft_fwd_fast(const float* __restrict__ x0, int C0, const float* __restrict__ x
 }  // namespace
 }  // namespace pdes
 
-extern "C" int pdes_dft_fwd(const float* x0, int C0, const float* x1, int C1, int B, int H, int W, int m1, int m2,
-                            const float* tables, int herm_scale, float* X, void* stream) {
-  using namespace pdes;
+namespace pdes {
+namespace {
+int dft_fwd_impl(const float* x0, int C0, const float* x1, int C1, int B, int H, int W, int m1, int m2,
+                 const float* tables, int herm_scale, float* X, float* X2f, int CinP, void* stream) {
+  float2* X2 = reinterpret_cast<float2*>(X2f);
   PDES_REQUIRE(x0 != nullptr && tables != nullptr && X != nullptr, PDES_ERR_ARG, "pdes_dft_fwd: null pointer");
   PDES_REQUIRE(B > 0 && C0 > 0 && C1 >= 0 && H > 0 && W > 0, PDES_ERR_ARG, "pdes_dft_fwd: non-positive size");
   PDES_REQUIRE((C1 == 0) == (x1 == nullptr), PDES_ERR_ARG, "pdes_dft_fwd: x1/C1 mismatch");
@@ -280,7 +288,7 @@ extern "C" int pdes_dft_fwd(const float* x0, int C0, const float* x1, int C1, in
   if (H == 96 && W == 64 && m1 == 10 && m2 == 10 && aligned16(x0) && (x1 == nullptr || aligned16(x1))) {
     auto kfast = k_dft_fwd_fast<96, 64, 10, 10>;
     PDES_LAUNCH(kfast, dim3((unsigned)(B * (C0 + C1))), dim3(128), 0, stream, x0, C0, x1, C1, tables + t.twa, t.nc4,
-                herm_scale ? tables + t.herm : nullptr, X);
+                herm_scale ? tables + t.herm : nullptr, X, X2, B, CinP);
     return check_launch("pdes_dft_fwd(fast)");
   }
   const int xs_stride = (W % 2 == 0) ? W + 1 : W;
@@ -298,6 +306,22 @@ extern "C" int pdes_dft_fwd(const float* x0, int C0, const float* x1, int C1, in
   if (smem > 48 * 1024) PDES_SET_SMEM(kfn, smem);
   const float* lscale = herm_scale ? tables + t.herm : nullptr;
   PDES_LAUNCH(kfn, dim3((unsigned)(B * (C0 + C1))), dim3(kK1Threads), smem, stream, x0, C0, x1, C1, H, W, m1, m2,
-              t.nc4, R, xs_stride, tables + t.twa, tables + t.twh, lscale, X);
+              t.nc4, R, xs_stride, tables + t.twa, tables + t.twh, lscale, X, X2, B, CinP);
   return check_launch("pdes_dft_fwd");
+}
+}  // namespace
+}  // namespace pdes
+
+extern "C" int pdes_dft_fwd(const float* x0, int C0, const float* x1, int C1, int B, int H, int W, int m1, int m2,
+                            const float* tables, int herm_scale, float* X, void* stream) {
+  return pdes::dft_fwd_impl(x0, C0, x1, C1, B, H, W, m1, m2, tables, herm_scale, X, nullptr, 0, stream);
+}
+
+/* K1 that also writes the mode-major copy X2[m][b][i_pad] (complex, i_pad = channels rounded up to 16) read by
+ * pdes_mix_tc_fwd; pad columns are left untouched (the consumer masks them). */
+extern "C" int pdes_dft_fwd2(const float* x0, int C0, const float* x1, int C1, int B, int H, int W, int m1, int m2,
+                             const float* tables, int herm_scale, float* X, float* X2, void* stream) {
+  using namespace pdes;
+  PDES_REQUIRE(X2 != nullptr, PDES_ERR_ARG, "pdes_dft_fwd2: null X2");
+  return dft_fwd_impl(x0, C0, x1, C1, B, H, W, m1, m2, tables, herm_scale, X, X2, (C0 + C1 + 15) / 16 * 16, stream);
 }

@@ -163,7 +163,7 @@ def _check_f32_cuda(name, t, ndim=None):
 
 class FNOBlockFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, h, vb, res, w1, w2, wc, bias, act, wpack_f=None, wpack_b=None):
+    def forward(ctx, h, vb, res, w1, w2, wc, bias, act, wpack_f=None, wpack_b=None, grad_on=True):
         lib = _lib()
         _check_f32_cuda("h", h, 4)
         _check_f32_cuda("variables_broadcast", vb, 4)
@@ -185,9 +185,10 @@ class FNOBlockFunction(torch.autograd.Function):
         res = None if res is None else res.contiguous()
         w1c, w2c = w1.contiguous(), w2.contiguous()
         dev = h.device
-        # needs_input_grad ignores grad mode: under torch.no_grad() (rollout, push-forward unroll) nothing is saved
-        # and K3b does not store the pre-activation
-        needs_grad = torch.is_grad_enabled() and any(ctx.needs_input_grad)
+        # needs_input_grad ignores grad mode (and grad mode is always off inside forward): the wrapper passes the caller's
+        # grad mode, so under torch.no_grad() (rollout, push-forward unroll) nothing is saved and K3b does not store
+        # the pre-activation
+        needs_grad = bool(grad_on) and any(ctx.needs_input_grad)
         with torch.cuda.device(dev):
             tab = tables_for(dev, H, W, m1, m2)
             wc2 = None
@@ -247,7 +248,7 @@ class FNOBlockFunction(torch.autograd.Function):
             _counters["launches"] += 5 + (1 if act != ACT_NONE else 0) + (2 if wc is not None else 0) + \
                 (1 if (wc is not None and wpack_b is None) else 0)
         d_res = (g_pre if act != ACT_NONE else g) if ctx.has_res else None
-        return dh, None, d_res, gw1, gw2, (None if dwc is None else dwc.view_as(wc)), dbias, None, None, None
+        return dh, None, d_res, gw1, gw2, (None if dwc is None else dwc.view_as(wc)), dbias, None, None, None, None
 
 
 def fno_block(h, vb, res, w1, w2, wc, bias, act: int = ACT_NONE):
@@ -258,7 +259,7 @@ def fno_block(h, vb, res, w1, w2, wc, bias, act: int = ACT_NONE):
         wpack_f = _pack_cache.get(wc, ("f", Cin, Cout), lambda: _pack_1x1(wc, Cin, Cout, True))
         if torch.is_grad_enabled() and (h.requires_grad or wc.requires_grad or w1.requires_grad):
             wpack_b = _pack_cache.get(wc, ("b", Cout, C0, 0), lambda: _pack_1x1(wc, Cout, C0, False))
-    return FNOBlockFunction.apply(h, vb, res, w1, w2, wc, bias, act, wpack_f, wpack_b)
+    return FNOBlockFunction.apply(h, vb, res, w1, w2, wc, bias, act, wpack_f, wpack_b, torch.is_grad_enabled())
 
 
 def act_code(module) -> int | None:
@@ -291,9 +292,8 @@ class GroupNormActFunction(torch.autograd.Function):
             _native.check(lib, lib.pdes_gn_act_forward(p(x), p(weight), p(bias), float(eps), p(y), p(stats), p(ws),
                                                        B, C, HW, groups, act, _stream()))
             _counters["launches"] += 3
-        if torch.is_grad_enabled():
-            ctx.save_for_backward(x, weight, bias, stats)
-            ctx.groups, ctx.act = groups, act
+        ctx.save_for_backward(x, weight, bias, stats)
+        ctx.groups, ctx.act = groups, act
         return y
 
     @staticmethod
@@ -446,9 +446,8 @@ class Conv1x1Function(torch.autograd.Function):
             st = _stream()
             _native.check(lib, lib.pdes_conv1x1_tc(p(x), Cin, p(pack), p(bias), None, p(out), N * HW, B, N, HW, ACT_NONE, st))
             _counters["launches"] += 1
-        if torch.is_grad_enabled():
-            ctx.save_for_backward(x, weight)
-            ctx.has_bias = bias is not None
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
         return out
 
     @staticmethod
