@@ -505,7 +505,7 @@ def run_legs(hx: Harness, args, wl: Workload = WL):
         ach = wl.block_bytes(B) / (fwd_us * 1e-6) / 1e9 if fwd_us else None
         traffic, traffic_src = recorded_traffic(B)
         cpu = None
-        if not args.no_extras and not args.no_cpu_baseline:
+        if not args.no_extras and not args.no_cpu_baseline and hx.world == 1:   # reported at N = 1 only (tier spec)
             cpu = cpu_baseline_sample(B, wl)
         line = {"metric": "train_samples_per_s", "value": t["value"], "unit": "samples/s", "n_gpus": hx.world,
                 "steps": args.steps, "warmup": t["warmup"], "ms_per_step": t["ms"] / args.steps, "higher_is_better": True,

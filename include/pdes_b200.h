@@ -68,6 +68,30 @@ int pdes_mix_dx(const float* GO, const float* w1, const float* w2, float* P, int
 int pdes_mix_dw(const float* X, const float* GO, float* gw1, float* gw2,
                 int B, int Cin, int Cout, int H, int m1, int m2, void* stream);
 
+/* ---- K2 on the 5th-generation tensor cores (tcgen05 + TMEM, TMA-staged tiles, 3xTF32 => fp32-faithful) -----------------
+ * The same einsum (proc_fno.py:253-255,266-269) as a per-mode real 2x2-block GEMM: output channel on the M side (TMEM
+ * lanes), N = (sample, re|im), K = input channel; D = Wr*[Xr|Xi] + Wi*[-Xi|Xr], so the weights are streamed once.
+ *   pdes_mix_tc_pack : packed master copy Wp[m][o][i_pad][re|im] (i_pad = Cin rounded up to 16, zero padded, rows the
+ *                      reference overwrites when 2*m1 > H stored as zero) of weights1/weights2; the caller rebuilds it
+ *                      when the parameters change (once per optimizer step; never during a rollout).  The parameters,
+ *                      their gradients, Adam and the all-reduce keep the reference layout.
+ *   pdes_dft_fwd2    : K1 that additionally writes the mode-major spectrum X2[m][b][i_pad] complex.
+ *   pdes_mix_tc_fwd  : O2[2][m][b][o] complex = mix(X2, Wp); partial 1 is only written for the work items that were
+ *                      split between two CTAs (the chunk stream is cut into equal ranges, one per SM).
+ *   pdes_inv_h_modes : K3a for that layout: Z[b][h][2l+ri][o] = sum_k e^{+2 pi i kx_k h/H} (O2[0] + O2[1] where split);
+ *                      `Cin` must be the reduction width pdes_mix_tc_fwd ran with.
+ * pdes_mix_tc_ok() == 0 (B > 32, tensor-core mode < 2, no TMA driver entry point) => use pdes_mix_fwd + pdes_inv_h. */
+int pdes_mix_tc_ok(int B, int Cin, int Cout, int m1, int m2);
+size_t pdes_mix_tc_pack_floats(int Cin, int Cout, int m1, int m2);
+size_t pdes_mix_tc_x2_floats(int B, int Cin, int m1, int m2);
+size_t pdes_mix_tc_o2_floats(int B, int Cout, int m1, int m2);
+int pdes_mix_tc_pack(const float* w1, const float* w2, float* Wp, int Cin, int Cout, int H, int m1, int m2, void* stream);
+int pdes_dft_fwd2(const float* x0, int C0, const float* x1, int C1, int B, int H, int W, int m1, int m2,
+                  const float* tables, int herm_scale, float* X, float* X2, void* stream);
+int pdes_mix_tc_fwd(const float* X2, const float* Wp, float* O2, int B, int Cin, int Cout, int m1, int m2, void* stream);
+int pdes_inv_h_modes(const float* O2, int B, int Cin, int C, int H, int m1, int m2, const float* tables, float* Z,
+                     void* stream);
+
 /* ---- K3a: inverse DFT along H -----------------------------------------------------------------------
  * Z[b][h][j][c] (c fastest, j = 2*l + {re,im}) = sum_k e^{+2 pi i kx_k h/H} * sum_s P[s][b][c][k][l].
  * First half of torch.fft.irfft2 (proc_fno.py:287), without ever building the zero-padded spectrum
@@ -179,13 +203,14 @@ int pdes_gn_act_backward(const float* dy, const float* x, const float* gamma, co
 /* ---- fused chains (what the nn.Module binding calls) ----------------------------------------------------
  * One FNO_Layer / U-FNO block tail, forward:  K1 -> K2 -> K3a -> K3b.
  *   h [B,C0,H,W], vb [B,C1,H,W] or NULL, w1/w2 complex [Cin][Cout][m1][m2], wc [Cout][Cin] = w.weight in its
- *   parameter layout (NULL = no 1x1), wpack = pdes_gemm_tc_pack_t(wc, Cin, Cin, Cout) cached by the caller per weight
+ *   parameter layout (NULL = no 1x1), wspec = pdes_mix_tc_pack(w1, w2) cached by the caller per weight version or NULL
+ *   (then K2 runs from the parameter layout on the FFMA kernels), wpack = pdes_gemm_tc_pack_t(wc, Cin, Cin, Cout) cached by the caller per weight
  *   version or NULL (then it is packed into the workspace on every call), bias [Cout] or NULL, res [B,Cout,H,W] or
  *   NULL (the U-Net branch), out [B,Cout,H,W], pre (NULL unless the backward will need it), Xsave [B][Cin][2MM]
  *   complex (kept for the backward), ws: pdes_block_fwd_workspace_floats() floats. */
 size_t pdes_block_fwd_workspace_floats(int B, int Cin, int Cout, int H, int W, int m1, int m2);
 int pdes_block_forward(const float* h, int C0, const float* vb, int C1, const float* w1, const float* w2,
-                       const float* wc, const float* wpack, const float* bias, const float* res,
+                       const float* wspec, const float* wc, const float* wpack, const float* bias, const float* res,
                        const float* tables, float* Xsave, float* ws, float* out, float* pre,
                        int B, int Cout, int H, int W, int m1, int m2, int act, void* stream);
 /* backward of the same block.  Inputs: g_out, pre (if act != none), h, vb, Xsave, w1, w2, wc [Cout][Cin],

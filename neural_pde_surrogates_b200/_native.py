@@ -31,6 +31,14 @@ _PROTOTYPES = {
     "pdes_mix_fwd": (c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "pdes_mix_dx": (c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "pdes_mix_dw": (c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "pdes_mix_tc_ok": (c_int, [_I, _I, _I, _I, _I]),
+    "pdes_mix_tc_pack_floats": (c_size_t, [_I, _I, _I, _I]),
+    "pdes_mix_tc_x2_floats": (c_size_t, [_I, _I, _I, _I]),
+    "pdes_mix_tc_o2_floats": (c_size_t, [_I, _I, _I, _I]),
+    "pdes_mix_tc_pack": (c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "pdes_dft_fwd2": (c_int, [_P, _I, _P, _I, _I, _I, _I, _I, _I, _P, _I, _P, _P, _P]),
+    "pdes_mix_tc_fwd": (c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "pdes_inv_h_modes": (c_int, [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
     "pdes_inv_h": (c_int, [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
     "pdes_inv_w_gemm": (c_int, [_P, _P, _I, _P, _I, _P, _I, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "pdes_set_tensor_core_mode": (None, [_I]),
@@ -61,7 +69,7 @@ _PROTOTYPES = {
     "pdes_gn_act_forward": (c_int, [_P, _P, _P, ctypes.c_float, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "pdes_gn_act_backward": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "pdes_block_fwd_workspace_floats": (c_size_t, [_I, _I, _I, _I, _I, _I, _I]),
-    "pdes_block_forward": (c_int, [_P, _I, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
+    "pdes_block_forward": (c_int, [_P, _I, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                                    _I, _I, _I, _I, _I, _I, _I, _P]),
     "pdes_block_bwd_workspace_floats": (c_size_t, [_I, _I, _I, _I, _I, _I, _I, _I]),
     "pdes_block_backward": (c_int, [_P, _P, _P, _I, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,

@@ -6,7 +6,7 @@
 namespace pdes {
 namespace {
 
-struct FwdWs { size_t P, Z, PK, WT, total; int nsplit; };
+struct FwdWs { size_t P, Z, PK, WT, X2, O2, total; int nsplit; };
 FwdWs fwd_ws(int B, int Cin, int Cout, int H, int W, int m1, int m2) {
   (void)W;
   FwdWs w;
@@ -16,7 +16,9 @@ FwdWs fwd_ws(int B, int Cin, int Cout, int H, int W, int m1, int m2) {
   w.Z = w.P + round4((size_t)w.nsplit * B * Cout * M2 * 2);
   w.PK = w.Z + round4((size_t)B * H * 2 * m2 * Cout);
   w.WT = w.PK + round4(pdes_gemm_tc_pack_floats(Cin, Cout));         // packed 1x1 weights (tensor-core mode)
-  w.total = w.WT + round4((size_t)Cin * Cout);                         // transposed 1x1 weights (FFMA mode)
+  w.X2 = w.WT + round4((size_t)Cin * Cout);                            // transposed 1x1 weights (FFMA mode)
+  w.O2 = w.X2 + round4(pdes_mix_tc_x2_floats(B, Cin, m1, m2));         // mode-major spectrum for K2 on tcgen05
+  w.total = w.O2 + round4(pdes_mix_tc_o2_floats(B, Cout, m1, m2));     // its output (two partials)
   return w;
 }
 
@@ -47,7 +49,8 @@ size_t pdes_block_fwd_workspace_floats(int B, int Cin, int Cout, int H, int W, i
 }
 
 int pdes_block_forward(const float* h, int C0, const float* vb, int C1, const float* w1, const float* w2,
-                       const float* wc, const float* wpack, const float* bias, const float* res, const float* tables,
+                       const float* wspec, const float* wc, const float* wpack, const float* bias, const float* res,
+                       const float* tables,
                        float* Xsave, float* ws, float* out, float* pre, int B, int Cout, int H, int W, int m1, int m2,
                        int act, void* stream) {
   using namespace pdes;
@@ -57,9 +60,18 @@ int pdes_block_forward(const float* h, int C0, const float* vb, int C1, const fl
   const FwdWs w = fwd_ws(B, Cin, Cout, H, W, m1, m2);
   float* P = ws + w.P;
   float* Z = ws + w.Z;
-  if (int e = pdes_dft_fwd(h, C0, vb, C1, B, H, W, m1, m2, tables, 0, Xsave, stream)) return e;
-  if (int e = pdes_mix_fwd(Xsave, w1, w2, P, w.nsplit, B, Cin, Cout, H, m1, m2, stream)) return e;
-  if (int e = pdes_inv_h(P, w.nsplit, B, Cout, H, m1, m2, tables, Z, stream)) return e;
+  if (wspec != nullptr && pdes_mix_tc_ok(B, Cin, Cout, m1, m2)) {
+    // K2 on tcgen05 from the packed master copy: K1 also writes the mode-major spectrum, K3a reads K2's layout
+    float* X2 = ws + w.X2;
+    float* O2 = ws + w.O2;
+    if (int e = pdes_dft_fwd2(h, C0, vb, C1, B, H, W, m1, m2, tables, 0, Xsave, X2, stream)) return e;
+    if (int e = pdes_mix_tc_fwd(X2, wspec, O2, B, Cin, Cout, m1, m2, stream)) return e;
+    if (int e = pdes_inv_h_modes(O2, B, Cin, Cout, H, m1, m2, tables, Z, stream)) return e;
+  } else {
+    if (int e = pdes_dft_fwd(h, C0, vb, C1, B, H, W, m1, m2, tables, 0, Xsave, stream)) return e;
+    if (int e = pdes_mix_fwd(Xsave, w1, w2, P, w.nsplit, B, Cin, Cout, H, m1, m2, stream)) return e;
+    if (int e = pdes_inv_h(P, w.nsplit, B, Cout, H, m1, m2, tables, Z, stream)) return e;
+  }
   if (wc != nullptr && pdes_get_tensor_core_mode() && pdes_inv_w_gemm_tc_ok(Cout, Cin, H, W, m2, h, vb)) {
     const float* PK = wpack;
     if (PK == nullptr) {                       // no cached operand: pack wc[o][i] as At[k = i][n = o] on the fly

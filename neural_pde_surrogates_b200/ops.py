@@ -35,11 +35,12 @@ class _PackCache:
         self._d = {}
         self.epoch = 0
 
-    def get(self, param, kind, build):
+    def get(self, param, kind, build, also=()):
+        """`also`: further parameters the packed operand depends on (their versions join the validity stamp)."""
         if param is None or torch.cuda.is_current_stream_capturing():
             return None
         key = id(param)
-        stamp = (param._version, param.data_ptr(), tuple(param.shape), self.epoch)
+        stamp = tuple((q._version, q.data_ptr(), tuple(q.shape)) for q in (param, *also)) + (self.epoch,)
         ent = self._d.get(key)
         if ent is None or ent[0]() is not param or ent[1] != stamp:
             ent = (weakref.ref(param, lambda _r, k=key, d=self._d: d.pop(k, None)), stamp, {})
@@ -145,6 +146,22 @@ def _pack_1x1(weight, K, N, transposed: bool, col_off: int = 0):
     return pack
 
 
+def _pack_spectral(w1, w2, H):
+    """pdes_mix_tc_pack: the packed master copy Wp[m][o][i_pad] of weights1 / weights2 for K2 on tcgen05."""
+    lib = _lib()
+    Cin, Cout, m1, m2 = w1.shape
+    a, b = w1.detach().contiguous(), w2.detach().contiguous()
+    wp = torch.empty(lib.pdes_mix_tc_pack_floats(Cin, Cout, m1, m2), dtype=torch.float32, device=w1.device)
+    _native.check(lib, lib.pdes_mix_tc_pack(a.data_ptr(), b.data_ptr(), wp.data_ptr(), Cin, Cout, H, m1, m2, _stream()))
+    _counters["launches"] += 1
+    _counters["spectral_packs"] = _counters.get("spectral_packs", 0) + 1
+    return wp
+
+
+# K2 on the tensor cores from the packed master copy (default); False keeps the FFMA kernels on the parameter layout
+enable_mix_tc = True
+
+
 def _tc_pack_usable(weight) -> bool:
     return (weight is not None and weight.is_cuda and weight.dtype == torch.float32
             and _lib().pdes_get_tensor_core_mode() >= 1)
@@ -163,7 +180,7 @@ def _check_f32_cuda(name, t, ndim=None):
 
 class FNOBlockFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, h, vb, res, w1, w2, wc, bias, act, wpack_f=None, wpack_b=None, grad_on=True):
+    def forward(ctx, h, vb, res, w1, w2, wc, bias, act, wpack_f=None, wpack_b=None, grad_on=True, wspec=None):
         lib = _lib()
         _check_f32_cuda("h", h, 4)
         _check_f32_cuda("variables_broadcast", vb, 4)
@@ -203,7 +220,7 @@ class FNOBlockFunction(torch.autograd.Function):
             p = lambda t: None if t is None else t.data_ptr()
             with _Timed("block_forward"):
                 _native.check(lib, lib.pdes_block_forward(
-                    p(h), C0, p(vb), C1, p(w1c), p(w2c), p(wc2), p(wpack_f), p(bias), p(res), p(tab), p(X), p(ws), p(out),
+                    p(h), C0, p(vb), C1, p(w1c), p(w2c), p(wspec), p(wc2), p(wpack_f), p(bias), p(res), p(tab), p(X), p(ws), p(out),
                     p(pre), B, Cout, H, W, m1, m2, act, _stream()))
             _counters["launches"] += 4 + (1 if (wc is not None and wpack_f is None) else 0)   # K1, K2, K3a, K3b (+ pack)
         if needs_grad:
@@ -248,7 +265,7 @@ class FNOBlockFunction(torch.autograd.Function):
             _counters["launches"] += 5 + (1 if act != ACT_NONE else 0) + (2 if wc is not None else 0) + \
                 (1 if (wc is not None and wpack_b is None) else 0)
         d_res = (g_pre if act != ACT_NONE else g) if ctx.has_res else None
-        return dh, None, d_res, gw1, gw2, (None if dwc is None else dwc.view_as(wc)), dbias, None, None, None, None
+        return dh, None, d_res, gw1, gw2, (None if dwc is None else dwc.view_as(wc)), dbias, None, None, None, None, None
 
 
 def fno_block(h, vb, res, w1, w2, wc, bias, act: int = ACT_NONE):
@@ -259,7 +276,17 @@ def fno_block(h, vb, res, w1, w2, wc, bias, act: int = ACT_NONE):
         wpack_f = _pack_cache.get(wc, ("f", Cin, Cout), lambda: _pack_1x1(wc, Cin, Cout, True))
         if torch.is_grad_enabled() and (h.requires_grad or wc.requires_grad or w1.requires_grad):
             wpack_b = _pack_cache.get(wc, ("b", Cout, C0, 0), lambda: _pack_1x1(wc, Cout, C0, False))
-    return FNOBlockFunction.apply(h, vb, res, w1, w2, wc, bias, act, wpack_f, wpack_b, torch.is_grad_enabled())
+    wspec = None
+    if enable_mix_tc and w1.is_cuda and h.is_cuda and h.dim() == 4:
+        lib = _lib()
+        Cin_, Cout_, m1, m2 = w1.shape
+        if lib.pdes_mix_tc_ok(h.shape[0], Cin_, Cout_, m1, m2):
+            H = h.shape[2]
+            with torch.cuda.device(h.device):
+                wspec = _pack_cache.get(w1, ("spec", H), lambda: _pack_spectral(w1, w2, H), also=(w2,))
+                if wspec is None:                                       # CUDA-graph capture: the pack is part of the graph
+                    wspec = _pack_spectral(w1, w2, H)
+    return FNOBlockFunction.apply(h, vb, res, w1, w2, wc, bias, act, wpack_f, wpack_b, torch.is_grad_enabled(), wspec)
 
 
 def act_code(module) -> int | None:

@@ -77,6 +77,85 @@ def check_mix(be, shape):
     return errs
 
 
+def mt_geom(B, Cin, Cout, m1, m2, sms=148):
+    """Python mirror of mt_geom() in csrc/spectral_mix_tc.cu (how K2 on tcgen05 cuts its chunk stream)."""
+    CinP = (Cin + 15) // 16 * 16
+    ntile = (Cout + 127) // 128
+    to = ((Cout + ntile - 1) // ntile + 7) // 8 * 8
+    nck = CinP // 16
+    nitems = 2 * m1 * m2 * ntile
+    nch = nitems * nck
+    G = max(min(sms, nitems), 1)
+    per = max((nch + G - 1) // G, nck)
+    split = np.array([(it * nck) // per != ((it + 1) * nck - 1) // per for it in range(nitems)])
+    return dict(CinP=CinP, ntile=ntile, to=to, nck=nck, nitems=nitems, per=per, split=split)
+
+
+def check_spectral_tc(be, shape, run_mma):
+    """The tensor-core K2 family: packed master copy of the weights, K1's mode-major spectrum, K3a on K2's output layout
+    (both builds) and, with run_mma (sm_100a only), the tcgen05 mix itself -- all against the float64 oracle."""
+    B, C0, C1, Cout, H, W, m1, m2 = shape
+    Cin, MM2 = C0 + C1, 2 * m1 * m2
+    lib = be.lib
+    rng = _rng(7)
+    g = mt_geom(B, Cin, Cout, m1, m2)
+    CinP = g["CinP"]
+    w1, w2 = _weights(rng, Cin, Cout, m1, m2)
+    dw1, dw2 = be.upload(w1), be.upload(w2)
+    # ---- packed master copy: Wp[m][o][i_pad] complex, dead rows and pad columns zero
+    assert lib.pdes_mix_tc_pack_floats(Cin, Cout, m1, m2) == MM2 * Cout * CinP * 2
+    Wp = be.empty((MM2, Cout, CinP), complex_=True)
+    be.check(lib.pdes_mix_tc_pack(be.ptr(dw1), be.ptr(dw2), be.ptr(Wp), Cin, Cout, H, m1, m2, be.stream))
+    wt = np.concatenate([w1, w2], axis=2) * so.live_rows(H, m1)[None, None, :, None]        # [Cin, Cout, 2m1, m2]
+    ref_wp = np.zeros((MM2, Cout, CinP), dtype=np.complex64)
+    ref_wp[:, :, :Cin] = wt.reshape(Cin, Cout, MM2).transpose(2, 1, 0)
+    assert np.array_equal(be.download(Wp), ref_wp), f"weight pack {shape}"
+    # ---- K1 with the mode-major copy
+    x0 = rng.standard_normal((B, C0, H, W)).astype(np.float32)
+    x1 = rng.standard_normal((B, C1, H, W)).astype(np.float32) if C1 else None
+    tab = be.tables(H, W, m1, m2)
+    dx0, dx1 = be.upload(x0), (be.upload(x1) if C1 else None)
+    X = be.empty((B, Cin, 2 * m1, m2), complex_=True)
+    assert lib.pdes_mix_tc_x2_floats(B, Cin, m1, m2) == MM2 * B * CinP * 2
+    X2 = be.empty((MM2, B, CinP), complex_=True)
+    be.check(lib.pdes_dft_fwd2(be.ptr(dx0), C0, be.ptr(dx1), C1, B, H, W, m1, m2, be.ptr(tab), 0, be.ptr(X), be.ptr(X2), be.stream))
+    Xh, X2h = be.download(X), be.download(X2)
+    xin = x0 if x1 is None else np.concatenate([x0, x1], axis=1)
+    assert so.rel_l2(Xh, so.dft_fwd_pruned(xin, m1, m2)) < TOL
+    assert np.array_equal(X2h[:, :, :Cin], Xh.reshape(B, Cin, MM2).transpose(2, 0, 1)), f"mode-major spectrum {shape}"
+    # ---- K2 on tcgen05 (or, without a GPU, a synthetic K2 output with the same partial-sum convention)
+    O_ref = so.mode_mix(Xh.astype(np.complex128), w1, w2, H)                                 # [B, Cout, 2m1, m2]
+    assert lib.pdes_mix_tc_o2_floats(B, Cout, m1, m2) == 2 * MM2 * B * Cout * 2
+    item_of = (np.arange(MM2)[:, None] * g["ntile"] + (np.arange(Cout)[None, :] // g["to"]))  # [m][o] -> work item
+    split_mo = g["split"][item_of]                                                            # [m][o]
+    if run_mma:
+        assert lib.pdes_mix_tc_ok(B, Cin, Cout, m1, m2) == 1
+        O2 = be.empty((2, MM2, B, Cout), complex_=True)                                       # NaN prefilled
+        be.check(lib.pdes_mix_tc_fwd(be.ptr(X2), be.ptr(Wp), be.ptr(O2), B, Cin, Cout, m1, m2, be.stream))
+        O2h = be.download(O2)
+        p1 = np.where(split_mo[:, None, :], O2h[1], 0)
+        assert np.isnan(O2h[1].real[~np.broadcast_to(split_mo[:, None, :], O2h[1].shape)]).all(), "partial 1 written for an unsplit item"
+        got = (O2h[0] + p1).transpose(1, 2, 0).reshape(B, Cout, 2 * m1, m2)
+        err = so.rel_l2(got, O_ref)
+        assert err < TOL, f"mix_tc {shape}: rel L2 {err:.3e}"
+    else:
+        Om = O_ref.reshape(B, Cout, MM2).transpose(2, 0, 1).astype(np.complex64)              # [m][b][o]
+        U = (rng.standard_normal(Om.shape) + 1j * rng.standard_normal(Om.shape)).astype(np.complex64)
+        sp = np.broadcast_to(split_mo[:, None, :], Om.shape)
+        O2h = np.stack([np.where(sp, Om - U, Om), np.where(sp, U, np.nan + 0j)]).astype(np.complex64)
+        O2 = be.upload(O2h)
+    # ---- K3a on that layout
+    Z = be.empty((B, H, 2 * m2, Cout))
+    be.check(lib.pdes_inv_h_modes(be.ptr(O2), B, Cin, Cout, H, m1, m2, be.ptr(tab), be.ptr(Z), be.stream))
+    kx = so.kx_table(H, m1)
+    E = np.exp(2j * np.pi * np.outer(np.arange(H), kx) / H)                                   # [H, 2m1]
+    Zc = np.einsum("hk,bokl->bhlo", E, O_ref)                                                 # [B, H, m2, Cout]
+    Zref = np.stack([Zc.real, Zc.imag], axis=3).reshape(B, H, 2 * m2, Cout)
+    err = so.rel_l2(be.download(Z), Zref)
+    assert err < TOL, f"inv_h_modes {shape}: rel L2 {err:.3e}"
+    return err
+
+
 def check_inverse(be, shape, with_gemm=True, act=1, backward_scale=0):
     """K3a + K3b against the oracle: spectral inverse (+ 1x1 conv + bias + residual + GELU)."""
     B, C0, C1, Cout, H, W, m1, m2 = shape
@@ -170,8 +249,9 @@ def block_inputs(shape, seed=5, reference_init=False):
     return d
 
 
-def run_block(be, shape, d, act=1, use_res=True, use_conv=True):
-    """Forward + backward of the fused chain; returns dict of numpy results."""
+def run_block(be, shape, d, act=1, use_res=True, use_conv=True, spec_pack=False):
+    """Forward + backward of the fused chain; returns dict of numpy results.  spec_pack=True hands the chain the
+    packed master copy of the spectral weights (=> K2 on tcgen05 where supported)."""
     B, C0, C1, Cout, H, W, m1, m2 = shape
     Cin = C0 + C1
     lib = be.lib
@@ -179,10 +259,14 @@ def run_block(be, shape, d, act=1, use_res=True, use_conv=True):
     up = {k: (be.upload(v) if v is not None else None) for k, v in d.items()}
     X = be.empty((B, Cin, 2 * m1, m2), complex_=True)
     ws = be.empty((lib.pdes_block_fwd_workspace_floats(B, Cin, Cout, H, W, m1, m2),))
+    wspec = None
+    if spec_pack:
+        wspec = be.empty((lib.pdes_mix_tc_pack_floats(Cin, Cout, m1, m2),))
+        be.check(lib.pdes_mix_tc_pack(be.ptr(up["w1"]), be.ptr(up["w2"]), be.ptr(wspec), Cin, Cout, H, m1, m2, be.stream))
     out = be.empty((B, Cout, H, W))
     pre = be.empty((B, Cout, H, W))
     be.check(lib.pdes_block_forward(be.ptr(up["h"]), C0, be.ptr(up["vb"]), C1, be.ptr(up["w1"]), be.ptr(up["w2"]),
-                                    be.ptr(up["wc"]) if use_conv else None, None, be.ptr(up["bias"]) if use_conv else None,
+                                    be.ptr(wspec), be.ptr(up["wc"]) if use_conv else None, None, be.ptr(up["bias"]) if use_conv else None,
                                     be.ptr(up["res"]) if use_res else None, be.ptr(tab), be.ptr(X), be.ptr(ws),
                                     be.ptr(out), be.ptr(pre), B, Cout, H, W, m1, m2, act, be.stream))
     wsb = be.empty((lib.pdes_block_bwd_workspace_floats(B, C0, C1, Cout, H, W, m1, m2),))
@@ -208,9 +292,9 @@ def run_block(be, shape, d, act=1, use_res=True, use_conv=True):
     return r
 
 
-def check_block(be, shape, act=1, use_res=True, use_conv=True, reference_init=False, tol=TOL):
+def check_block(be, shape, act=1, use_res=True, use_conv=True, reference_init=False, tol=TOL, spec_pack=False):
     d = block_inputs(shape, reference_init=reference_init)
-    r = run_block(be, shape, d, act=act, use_res=use_res, use_conv=use_conv)
+    r = run_block(be, shape, d, act=act, use_res=use_res, use_conv=use_conv, spec_pack=spec_pack)
     actn = "gelu" if act else None
     wc = d["wc"] if use_conv else None
     bias = d["bias"] if use_conv else None

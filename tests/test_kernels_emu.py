@@ -43,6 +43,12 @@ def test_block_fwd_bwd(be, shape):
     kc.check_block(be, shape, act=1, use_res=True, use_conv=True)
 
 
+@pytest.mark.parametrize("shape", kc.SMALL_SHAPES + [(3, 20, 1, 140, 12, 8, 3, 4)])
+def test_spectral_tc_host_side(be, shape):
+    """weight pack, K1's mode-major copy and K3a on the tcgen05 K2's output layout (the MMA kernel itself is GPU-only)."""
+    kc.check_spectral_tc(be, shape, run_mma=False)
+
+
 def test_block_variants(be):
     kc.check_block(be, kc.SMALL_SHAPES[2], act=0, use_res=False, use_conv=True)    # FNO layer without activation
     kc.check_block(be, kc.SMALL_SHAPES[1], act=1, use_res=False, use_conv=True)    # pure FNO layer (GELU inside)

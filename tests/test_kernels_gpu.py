@@ -39,6 +39,20 @@ def test_mix_tma_configs(be, shape):
     kc.check_mix(be, shape)
 
 
+# K2 on tcgen05: small edge-case shapes (Nyquist column, dead rows, odd sizes), two output-channel tiles (Cout 140),
+# B > 8 (N = 32), B = 32 (N = 64, the widest accumulator), and the shipped shape at the bench batch
+@pytest.mark.parametrize("shape", kc.SMALL_SHAPES + [(3, 20, 1, 140, 12, 8, 3, 4), (16, 24, 1, 20, 16, 16, 4, 5),
+                                                     (32, 17, 0, 9, 8, 8, 2, 3), (4, 192, 1, 192, 96, 64, 10, 10),
+                                                     (16, 192, 1, 192, 96, 64, 10, 10)])
+def test_spectral_tc(be, shape):
+    kc.check_spectral_tc(be, shape, run_mma=True)
+
+
+@pytest.mark.parametrize("shape", kc.SMALL_SHAPES + FULL_SHAPES)
+def test_block_fwd_bwd_packed_spectral_weights(be, shape):
+    kc.check_block(be, shape, act=1, use_res=True, use_conv=True, spec_pack=True)
+
+
 @pytest.mark.parametrize("shape", kc.SMALL_SHAPES)
 def test_inverse_full(be, shape):
     kc.check_inverse(be, shape, with_gemm=True, act=1)

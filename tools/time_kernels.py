@@ -79,6 +79,28 @@ def main():
         wgws = torch.empty(lib.pdes_wgrad_workspace_floats(B, Cout, Cin, HW), device=dev)
         p = lambda t: t.data_ptr()
         ck = lambda c: _native.check(lib, c)
+        wsp = torch.empty(lib.pdes_mix_tc_pack_floats(Cin, Cout, m1, m2), device=dev)
+        X2 = torch.zeros(lib.pdes_mix_tc_x2_floats(B, Cin, m1, m2), device=dev)
+        O2 = torch.zeros(lib.pdes_mix_tc_o2_floats(B, Cout, m1, m2), device=dev)
+        ck(lib.pdes_mix_tc_pack(p(w1), p(w2), p(wsp), Cin, Cout, H, m1, m2, st))
+        pack1 = torch.empty(lib.pdes_gemm_tc_pack_floats(Cin, Cout), device=dev)
+        ck(lib.pdes_gemm_tc_pack_t(p(wc), Cin, Cin, Cout, p(pack1), st))
+        tc_runs = {
+            "K1_dft_fwd2_modemajor": (lambda: ck(lib.pdes_dft_fwd2(p(h), C0, p(vb), C1, B, H, W, m1, m2, p(tab), 0, p(X), p(X2), st)),
+                                      4 * B * Cin * HW + 16 * B * Cin * 2 * MM),
+            "K2_mix_tcgen05": (lambda: ck(lib.pdes_mix_tc_fwd(p(X2), p(wsp), p(O2), B, Cin, Cout, m1, m2, st)),
+                               16 * Cin * Cout * MM + 8 * B * Cin * 2 * MM + 8 * B * Cout * 2 * MM),
+            "K3a_inv_h_modes": (lambda: ck(lib.pdes_inv_h_modes(p(O2), B, Cin, Cout, H, m1, m2, p(tab), p(Z), st)),
+                                8 * B * Cout * 2 * MM + 4 * B * H * 2 * m2 * Cout),
+            "spectral_weight_pack": (lambda: ck(lib.pdes_mix_tc_pack(p(w1), p(w2), p(wsp), Cin, Cout, H, m1, m2, st)),
+                                     32 * Cin * Cout * MM),
+            "block_forward_tc_cached_packs": (lambda: ck(lib.pdes_block_forward(p(h), C0, p(vb), C1, p(w1), p(w2), p(wsp), p(wc), p(pack1), p(bias),
+                                                                                p(res), p(tab), p(X), p(ws), p(outp), None, B, Cout, H, W, m1, m2, 1, st)),
+                                              4 * B * Cin * HW + 16 * Cin * Cout * MM + 8 * B * Cout * HW + 4 * Cout * Cin + 4 * Cout),
+            "block_forward_tc_with_pre": (lambda: ck(lib.pdes_block_forward(p(h), C0, p(vb), C1, p(w1), p(w2), p(wsp), p(wc), p(pack1), p(bias),
+                                                                            p(res), p(tab), p(X), p(ws), p(outp), p(pre), B, Cout, H, W, m1, m2, 1, st)),
+                                          4 * B * Cin * HW + 16 * Cin * Cout * MM + 8 * B * Cout * HW + 4 * Cout * Cin + 4 * Cout),
+        }
         runs = {
             "K1_dft_fwd": (lambda: ck(lib.pdes_dft_fwd(p(h), C0, p(vb), C1, B, H, W, m1, m2, p(tab), 0, p(X), st)),
                            4 * B * Cin * HW + 8 * B * Cin * 2 * MM),
@@ -93,7 +115,7 @@ def main():
                                             ck(lib.pdes_inv_w_gemm_tc(p(Z), p(pack), p(h), C0, p(vb), C1, p(bias), p(res), p(tab), 0,
                                                                       p(outp), None, B, Cout, H, W, m1, m2, 1, st))),
                                    4 * B * Cin * HW + 8 * B * Cout * HW + 4 * B * H * 2 * m2 * Cout),
-            "block_forward": (lambda: ck(lib.pdes_block_forward(p(h), C0, p(vb), C1, p(w1), p(w2), p(wc), None, p(bias), p(res),
+            "block_forward": (lambda: ck(lib.pdes_block_forward(p(h), C0, p(vb), C1, p(w1), p(w2), None, p(wc), None, p(bias), p(res),
                                                                 p(tab), p(X), p(ws), p(outp), None, B, Cout, H, W, m1, m2, 1, st)),
                               4 * B * Cin * HW + 16 * Cin * Cout * MM + 8 * B * Cout * HW + 4 * Cout * Cin + 4 * Cout),
             "act_bwd": (lambda: ck(lib.pdes_act_bwd(p(g), p(pre), p(gpre), g.numel(), 1, st)), 12 * B * Cout * HW),
@@ -109,7 +131,12 @@ def main():
                                4 * B * (3 * Cout + 2 * Cin + C0) * HW + 32 * Cin * Cout * MM),
         }
         pre.copy_(torch.randn_like(pre))
+        only = os.environ.get("PDES_TIME_ONLY")
+        if lib.pdes_mix_tc_ok(B, Cin, Cout, m1, m2):
+            runs = {**tc_runs, **runs}
         for name, (fn, nbytes) in runs.items():
+            if only and not any(t in name for t in only.split(",")):
+                continue
             us = timeit(fn, flush=flush)
             us_hot = timeit(fn)
             gbs = nbytes / us / 1e3
@@ -117,7 +144,7 @@ def main():
                                        GBps=round(gbs, 1), frac_of_measured_hbm=round(gbs / PEAK, 3))
             print(f"B={B:2d} {name:16s} cold {us:9.2f} us  hot {us_hot:9.2f} us  {nbytes/1e6:8.2f} MB  {gbs:8.1f} GB/s  {gbs/PEAK:6.3f}")
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    json.dump(out, open(os.path.join(ROOT, "gpurun_out", "kernel_times.json"), "w"), indent=1)
+    json.dump(out, open(os.path.join(ROOT, "gpurun_out", os.environ.get("PDES_TIME_OUT", "kernel_times.json")), "w"), indent=1)
 
 
 if __name__ == "__main__":
