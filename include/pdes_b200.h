@@ -71,8 +71,10 @@ int pdes_mix_dw(const float* X, const float* GO, float* gw1, float* gw2,
 /* ---- K2 on the 5th-generation tensor cores (tcgen05 + TMEM, TMA-staged tiles, 3xTF32 => fp32-faithful) -----------------
  * The same einsum (proc_fno.py:253-255,266-269) as a per-mode real 2x2-block GEMM: output channel on the M side (TMEM
  * lanes), N = (sample, re|im), K = input channel; D = Wr*[Xr|Xi] + Wi*[-Xi|Xr], so the weights are streamed once.
- *   pdes_mix_tc_pack : packed master copy Wp[m][o][i_pad][re|im] (i_pad = Cin rounded up to 16, zero padded, rows the
- *                      reference overwrites when 2*m1 > H stored as zero) of weights1/weights2; the caller rebuilds it
+ *   pdes_mix_tc_pack : packed master copy Wp[m][tile][chunk][row][16 i][re|im] (<= 128 output channels per tile, 16
+ *                      input channels per chunk, zero padded: every chunk is one contiguous block of 128-byte rows in
+ *                      the order the kernel streams them; rows the reference overwrites when 2*m1 > H stored as
+ *                      zero) of weights1/weights2; the caller rebuilds it
  *                      when the parameters change (once per optimizer step; never during a rollout).  The parameters,
  *                      their gradients, Adam and the all-reduce keep the reference layout.
  *   pdes_dft_fwd2    : K1 that additionally writes the mode-major spectrum X2[m][b][i_pad] complex.

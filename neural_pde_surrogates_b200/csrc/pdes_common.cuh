@@ -11,6 +11,17 @@
   kernel<<<(grid), (block), (smem), (cudaStream_t)(stream)>>>(__VA_ARGS__)
 #define PDES_SET_SMEM(kernel, bytes) \
   cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))
+// Ask for the maximum shared-memory carve-out for a kernel of the block chain (once per call site).  The tcgen05 kernels
+// need ~220 KB of shared memory; a neighbour that runs with the default (small) carve-out forces the SMs to drain and
+// switch their L1 / shared-memory split at every kernel boundary of the chain.
+#define PDES_MAX_CARVEOUT(kernel)                                                                      \
+  do {                                                                                                 \
+    static bool _pdes_done = false;                                                                    \
+    if (!_pdes_done) {                                                                                 \
+      cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared); \
+      _pdes_done = true;                                                                               \
+    }                                                                                                  \
+  } while (0)
 #endif
 
 #include <cstddef>

@@ -91,5 +91,6 @@ static inline const char* cudaGetErrorString(cudaError_t) { return "emu"; }
 #define PDES_LAUNCH(kernel, grid, block, smem, stream, ...) \
   pdes_emu::launch((grid), (block), (smem), [&]() { kernel(__VA_ARGS__); })
 #define PDES_SET_SMEM(kernel, bytes) (0)
+#define PDES_MAX_CARVEOUT(kernel) do { } while (0)
 
 #endif  // PDES_CPU_EMU

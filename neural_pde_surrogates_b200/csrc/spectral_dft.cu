@@ -287,6 +287,7 @@ int dft_fwd_impl(const float* x0, int C0, const float* x1, int C1, int B, int H,
   const TableLayout t = table_layout(H, W, m1, m2);
   if (H == 96 && W == 64 && m1 == 10 && m2 == 10 && aligned16(x0) && (x1 == nullptr || aligned16(x1))) {
     auto kfast = k_dft_fwd_fast<96, 64, 10, 10>;
+    PDES_MAX_CARVEOUT(kfast);
     PDES_LAUNCH(kfast, dim3((unsigned)(B * (C0 + C1))), dim3(128), 0, stream, x0, C0, x1, C1, tables + t.twa, t.nc4,
                 herm_scale ? tables + t.herm : nullptr, X, X2, B, CinP);
     return check_launch("pdes_dft_fwd(fast)");
@@ -304,6 +305,7 @@ int dft_fwd_impl(const float* x0, int C0, const float* x1, int C1, int B, int H,
   const size_t smem = bytes_for(R);
   auto kfn = k_dft_fwd;
   if (smem > 48 * 1024) PDES_SET_SMEM(kfn, smem);
+  PDES_MAX_CARVEOUT(kfn);
   const float* lscale = herm_scale ? tables + t.herm : nullptr;
   PDES_LAUNCH(kfn, dim3((unsigned)(B * (C0 + C1))), dim3(kK1Threads), smem, stream, x0, C0, x1, C1, H, W, m1, m2,
               t.nc4, R, xs_stride, tables + t.twa, tables + t.twh, lscale, X, X2, B, CinP);

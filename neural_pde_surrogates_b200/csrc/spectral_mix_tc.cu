@@ -13,8 +13,10 @@
 // (16 * Cin * Cout * m1 * m2 bytes); the tensor pipe is a few percent busy by construction.
 //
 // Layouts
-//   Wp  packed master copy  [m][o][i_pad][re|im] fp32, i_pad = Cin rounded up to 16, zero padded; rows of the first
-//       weight block that the reference overwrites when 2*m1 > H (proc_fno.py:266-269) are stored as zeros.  Built by
+//   Wp  packed master copy  [m][tile][chunk][row][16 i][re|im] fp32 (tile = <= 128 output channels, chunk = 16 input
+//       channels, i padded to a multiple of 16 with zeros): one contiguous 128-byte-row block per chunk, in the order
+//       the kernel streams them; rows of the first weight block that the reference overwrites when 2*m1 > H
+//       (proc_fno.py:266-269) are stored as zeros.  Built by
 //       pdes_mix_tc_pack() once per weight version (the caller caches it); the parameters themselves, Adam and the
 //       gradient all-reduce keep the reference layout [Cin][Cout][m1][m2].
 //   X2  [m][b][i_pad] complex, mode-major copy of the retained spectrum written by K1 (pad columns are never read
@@ -39,6 +41,7 @@
 #include "pdes_ptx.cuh"
 #ifndef PDES_CPU_EMU
 #include <cuda.h>
+#include <cstdlib>
 #include <cstring>
 #endif
 
@@ -55,15 +58,17 @@ __host__ __device__ inline int mt_to(int Cout) { const int nt = mt_ntile(Cout); 
 namespace {
 
 // ------------------------------------------------------------------------------------------------- weight pack
-// [Cin][Cout][m1*m2] complex (x2 blocks) -> Wp[m][o][i_pad] complex.  Per output channel this is a 2-D transpose between
-// the input-channel and the mode index: a 32 x 32 tile goes through shared memory so that both the loads (along the
-// mode index) and the stores (along i) are coalesced.
+// [Cin][Cout][m1*m2] complex (x2 blocks) -> Wp[m][tile][chunk][row][16 i][re|im]: one (mode, output-channel tile, 16-channel
+// chunk) = `to` rows x 128 bytes = ONE CONTIGUOUS block, and the blocks sit in exactly the order the kernel streams them,
+// so every CTA reads one contiguous region of HBM (strided 128-byte rows reached only 2.4 TB/s: DRAM page misses).
+// Per output channel this is a 2-D transpose between the input-channel and the mode index: a 32 x 32 tile goes through
+// shared memory so that the loads (along the mode index) and the stores (128-byte segments along i) are coalesced.
 __global__ void __launch_bounds__(256)
 k_mix_tc_pack(const float2* __restrict__ w1, const float2* __restrict__ w2, float2* __restrict__ Wp, int Cin, int Cout,
-              int CinP, int m1, int m2, int H) {
+              int CinP, int m1, int m2, int H, int ntile, int to) {
   __shared__ float2 tile[32][33];
   const int MM = m1 * m2;
-  const int o = blockIdx.x;
+  const int o = blockIdx.x;                                             // 0 .. ntile*to - 1 (rows >= Cout are zero padding)
   const int i0 = blockIdx.y * 32;
   const int mt_per_half = (MM + 31) / 32;
   const int half = blockIdx.z / mt_per_half, mm0 = (blockIdx.z % mt_per_half) * 32;
@@ -72,17 +77,20 @@ k_mix_tc_pack(const float2* __restrict__ w1, const float2* __restrict__ w2, floa
   for (int r = ty; r < 32; r += 8) {                                  // r = input channel, tx = mode
     const int i = i0 + r, mm = mm0 + tx;
     float2 v = make_float2(0.f, 0.f);
-    if (i < Cin && mm < MM) v = __ldg(w + ((size_t)i * Cout + o) * MM + mm);
+    if (i < Cin && mm < MM && o < Cout) v = __ldg(w + ((size_t)i * Cout + o) * MM + mm);
     tile[r][tx] = v;
   }
   __syncthreads();
+  const int nck = CinP / kMtBK;
+  const int t = o / to, row = o - t * to;
   for (int r = ty; r < 32; r += 8) {                                  // r = mode, tx = input channel
     const int mm = mm0 + r, i = i0 + tx;
     if (mm < MM && i < CinP) {
       const int k = half * m1 + mm / m2;
       float2 v = tile[tx][r];
       if (row_dead(k, m1, H)) v = make_float2(0.f, 0.f);
-      Wp[((size_t)(half * MM + mm) * Cout + o) * CinP + i] = v;
+      const int m = half * MM + mm, kc = i / kMtBK, ii = i - kc * kMtBK;
+      Wp[((((size_t)m * ntile + t) * nck + kc) * to + row) * kMtBK + ii] = v;
     }
   }
 }
@@ -98,53 +106,74 @@ __device__ __forceinline__ bool item_is_split(const SplitRule& r, int item) {
   return (item * r.nck) / r.per != ((item + 1) * r.nck - 1) / r.per;
 }
 
-constexpr int kIh2Threads = 128, kIh2HP = 4;           // row pairs per thread per pass
-__global__ void __launch_bounds__(kIh2Threads)
+// Rows +kx and -kx are folded as well: with S_j = O[kx=j] + O[kx=-j], D_j = O[kx=j] - O[kx=-j] (j = 0..m1; j = 0 has no
+// partner, j = m1 only the negative one) the sums run over m1 + 1 terms instead of 2*m1:
+//     P = sum_j cos(2 pi j h/H) S_j,  Q = sum_j sin(2 pi j h/H) D_j.
+// Each thread keeps HP = 8 row pairs in registers (32 accumulators), so one spectrum load and four 128-bit twiddle loads
+// feed 32 FMAs.
+constexpr int kIh2HP = 8;                                // row pairs per thread
+constexpr int kIh2MaxWarps = 16;
+__global__ void __launch_bounds__(32 * kIh2MaxWarps)
 k_inv_h2(const float2* __restrict__ O2, SplitRule rule, int B, int C, int H, int m1, int m2,
          const float* __restrict__ twh_g, float* __restrict__ Z) {
   PDES_DYN_SMEM(float2, sm2);
-  const int K = 2 * m1, M2 = K * m2, J = 2 * m2;
+  const int K = 2 * m1, M2 = K * m2, J = 2 * m2, NJ = m1 + 1;
   const int npair = H / 2 + 1;
-  float2* Os = sm2;                                    // [K][32]
-  float2* tw = Os + (size_t)K * 32;                    // [npair][K]
-  const int tid = threadIdx.x, lane = tid & 31, wq = tid >> 5;
+  const int npp = (npair + kIh2HP - 1) / kIh2HP * kIh2HP;        // pairs padded to the register block
+  float2* Ss = sm2;                                    // [NJ][32]
+  float2* Ds = Ss + (size_t)NJ * 32;                   // [NJ][32]
+  float2* tw = Ds + (size_t)NJ * 32;                   // [NJ][npp]  (cos, sin)(2 pi j p / H)
+  const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, wq = tid >> 5, nwarp = nthr >> 5;
   const int o0 = blockIdx.x * 32, l = blockIdx.y, b = blockIdx.z;
   const int o = o0 + lane;
-  for (int idx = tid; idx < npair * K; idx += kIh2Threads) {
-    const int p = idx / K, k = idx - p * K;
-    const int j = (int)(((long long)kx_of(k, m1, H) * p) % H);
-    tw[idx] = make_float2(__ldg(twh_g + 2 * j), __ldg(twh_g + 2 * j + 1));
+  for (int idx = tid; idx < NJ * npp; idx += nthr) {
+    const int j = idx / npp, pp = idx - j * npp;
+    const int p = pp < npair ? pp : 0;
+    const int t = (int)(((unsigned)j * (unsigned)p) % (unsigned)H);
+    tw[idx] = make_float2(__ldg(twh_g + 2 * t), __ldg(twh_g + 2 * t + 1));
   }
   const size_t pstride = (size_t)M2 * B * C;
-  for (int idx = tid; idx < K * 32; idx += kIh2Threads) {
-    const int k = idx >> 5, oo = o0 + (idx & 31);
-    float2 v = make_float2(0.f, 0.f);
+  auto load_o = [&](int k, int oo) -> float2 {         // O[k][l] of channel oo (both partials where the item was split)
+    const int m = k * m2 + l;
+    const size_t at = ((size_t)m * B + b) * C + oo;
+    float2 v = __ldg(O2 + at);
+    if (item_is_split(rule, m * rule.ntile + oo / rule.to)) {
+      const float2 u = __ldg(O2 + pstride + at);
+      v.x += u.x; v.y += u.y;
+    }
+    return v;
+  };
+  for (int idx = tid; idx < NJ * 32; idx += nthr) {
+    const int j = idx >> 5, oo = o0 + (idx & 31);
+    float2 sv = make_float2(0.f, 0.f), dv = make_float2(0.f, 0.f);
     if (oo < C) {
-      const int m = k * m2 + l;
-      const size_t at = ((size_t)m * B + b) * C + oo;
-      v = __ldg(O2 + at);
-      if (item_is_split(rule, m * rule.ntile + oo / rule.to)) {
-        const float2 u = __ldg(O2 + pstride + at);
-        v.x += u.x; v.y += u.y;
+      if (j < m1) {                                    // +kx = j lives in row k = j
+        const float2 a = load_o(j, oo);
+        sv = a; dv = a;
+      }
+      if (j > 0) {                                     // -kx = -j lives in row k = 2*m1 - j
+        const float2 c = load_o(K - j, oo);
+        sv.x += c.x; sv.y += c.y; dv.x -= c.x; dv.y -= c.y;
       }
     }
-    Os[idx] = v;
+    Ss[idx] = sv;
+    Ds[idx] = dv;
   }
   __syncthreads();
-  for (int p0 = wq * kIh2HP; p0 < npair; p0 += 4 * kIh2HP) {
+  for (int p0 = wq * kIh2HP; p0 < npair; p0 += nwarp * kIh2HP) {
     float pr[kIh2HP], pi[kIh2HP], qr[kIh2HP], qi[kIh2HP];
 #pragma unroll
     for (int e = 0; e < kIh2HP; ++e) pr[e] = pi[e] = qr[e] = qi[e] = 0.0f;
-    for (int k = 0; k < K; ++k) {
-      const float2 ov = Os[k * 32 + lane];
+    for (int j = 0; j < NJ; ++j) {
+      const float2 sv = Ss[j * 32 + lane], dv = Ds[j * 32 + lane];
+      const float4* t4 = reinterpret_cast<const float4*>(tw + (size_t)j * npp + p0);       // warp-uniform: broadcast
 #pragma unroll
-      for (int e = 0; e < kIh2HP; ++e) {
-        const int p = (p0 + e < npair) ? (p0 + e) : (npair - 1);
-        const float2 t = tw[p * K + k];                                   // warp-uniform address: broadcast
-        pr[e] = fmaf(t.x, ov.x, pr[e]);
-        pi[e] = fmaf(t.x, ov.y, pi[e]);
-        qr[e] = fmaf(t.y, ov.x, qr[e]);
-        qi[e] = fmaf(t.y, ov.y, qi[e]);
+      for (int e = 0; e < kIh2HP; e += 2) {
+        const float4 t = t4[e >> 1];                                       // (cos, sin) of pairs p0+e, p0+e+1
+        pr[e] = fmaf(t.x, sv.x, pr[e]);         pi[e] = fmaf(t.x, sv.y, pi[e]);
+        qr[e] = fmaf(t.y, dv.x, qr[e]);         qi[e] = fmaf(t.y, dv.y, qi[e]);
+        pr[e + 1] = fmaf(t.z, sv.x, pr[e + 1]); pi[e + 1] = fmaf(t.z, sv.y, pi[e + 1]);
+        qr[e + 1] = fmaf(t.w, dv.x, qr[e + 1]); qi[e + 1] = fmaf(t.w, dv.y, qi[e + 1]);
       }
     }
     if (o < C) {
@@ -169,49 +198,79 @@ k_inv_h2(const float2* __restrict__ O2, SplitRule rule, int B, int C, int H, int
 
 #ifndef PDES_CPU_EMU
 // ------------------------------------------------------------------------------------------------- K2 on tcgen05
-constexpr int kMtThreads = 448, kMtMmaWarp = 12, kMtTmaWarp = 13;
-constexpr int kMtNST = 4;                              // TMEM A stages / shared-memory B stages
-constexpr int kMtMaxRaw = 8;
+// Facts measured on B200 that shape this kernel (tools/ubench_mma2.cu, tools/ablate_mix.py, profiles/r02_k2_*):
+//   * kind::tf32 TRUNCATES its operands (feeding unmasked fp32 bits gives bit-identical results), so the "hi" half of
+//     the 3xTF32 split needs no conversion at all: the MMA reads the raw fp32 tile the TMA delivered;
+//   * one thread cannot issue a small-N tcgen05.mma faster than every ~49 cycles (N = 32: tensor-pipe floor 16), four
+//     issuing warps reach ~18 cycles per MMA;
+//   * every scalar instruction of a single-thread role is latency-exposed (a runtime integer division ~150 cycles), and
+//     one loop iteration of any role costs several hundred cycles of mbarrier round trips.
+// Hence: the K index of the GEMM is the interleaved (input channel, re|im) pair exactly as it sits in the packed
+// weights, A_hi = the raw 128-byte-swizzled TMA tile in shared memory, only A_lo = W - trunc(W) goes through registers
+// into tensor memory; 16 convert warps / 4 issuing warps each own every fourth chunk (and its two ring stages), and all
+// per-chunk index arithmetic is strength-reduced to counters.
+//
+//   D[o, n] = sum_{k = (i, re|im)} Wp[o][k] * Bx[n][k],   Bx[(b,re)][(i,re|im)] = (Xr, -Xi),  Bx[(b,im)][(i,re|im)] = (Xi, Xr)
+constexpr int kMtCvtWarps = 16, kMtEpi0 = 16, kMtIssue0 = 20, kMtNIssue = 4, kMtTma0 = 24;
+constexpr int kMtThreads = 32 * 28;
+constexpr int kMtMaxStages = 8;
 
 struct MtBars {
-  unsigned long long full[kMtNST], empty[kMtNST], raw_full[kMtMaxRaw], raw_empty[kMtMaxRaw], acc_full[2], acc_empty[2];
+  unsigned long long raw_full[kMtMaxStages], full[kMtMaxStages], empty[kMtMaxStages], acc_full[2], acc_empty[2];
 };
 
 struct MtParams {
   float2* O2;
-  int B, Cin, Cout, CinP, nmodes, npad, bp, ntile, to, nck, per, nch_total, nraw;
+  int B, Cin, Cout, CinP, nmodes, npad, bp, ntile, to, nck, per, nch_total, nst, nbuf;
+  uint32_t stage_bytes, x_off, b_off;
+  int dbg;       // diagnostic builds (-DPDES_MT_ABLATE) only: 1 no MMA, 2 no TMA, 4 no convert work, 8 no epilogue stores
 };
+#ifdef PDES_MT_ABLATE
+#define MT_DBG(bit) ((p.dbg & (bit)) != 0)
+__device__ long long g_mt_trace[3 * 64 * 4];          // [role: 0 producer, 1 convert, 2 MMA][chunk < 64][4 stamps], CTA 0
+#define MT_TRACE(role, g, k) do { if (blockIdx.x == 0 && (g) < 64) g_mt_trace[((role) * 64 + (g)) * 4 + (k)] = clock64(); } while (0)
+#else
+#define MT_DBG(bit) false
+#define MT_TRACE(role, g, k) do { } while (0)
+#endif
 
 __device__ __forceinline__ float mt_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+// shared-memory matrix descriptor, K-major, 128-byte swizzle (8-row x 128-byte atoms 1024 bytes apart), sm_100 version
+__device__ __forceinline__ uint64_t mt_desc_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;                      // leading byte offset: unused for a K extent within one swizzle span
+  d |= (uint64_t)(1024 >> 4) << 32;            // stride byte offset: next 8-row group
+  d |= (uint64_t)1 << 46;                      // descriptor version 1 (Blackwell)
+  d |= (uint64_t)2 << 61;                      // SWIZZLE_128B
+  return d;
+}
 
 __global__ void __launch_bounds__(kMtThreads, 1)
 k_mix_tc(MtParams p, const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x) {
   PDES_DYN_SMEM(unsigned char, smem_raw);
   unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int npad = p.npad;
-  const uint32_t w_slot = 128u * 128u;                                     // 16 KB: [128 rows][128 B], rows >= TO unused
-  const uint32_t x_slot = (uint32_t)p.bp * 128u;                           // [bp rows][16 complex]
-  const uint32_t raw_slot = w_slot + ((x_slot + 1023u) & ~1023u);
-  const uint32_t lbo = (uint32_t)(npad / 8) * 128u + 16u;                  // +16: the 4 k-quads of a row fall in different banks
-  const uint32_t blk = 4u * lbo;                                           // one canonical [npad x 16] block
-  const uint32_t b_stage = 4u * blk;                                       // XA_hi, XA_lo, XB_hi, XB_lo
-  unsigned char* sRaw = base;
-  unsigned char* sB = sRaw + (size_t)p.nraw * raw_slot;
+  const uint32_t lbo = (uint32_t)(npad / 8) * 128u + 16u;                  // +16: the k-quads of a row fall in different banks
+  const uint32_t blk = 8u * lbo;                                           // one canonical [npad x 32] block (8 k-quads)
+  const uint32_t stage_bytes = p.stage_bytes, x_off = p.x_off, b_off = p.b_off;   // stage: [W raw 16 KB][X raw][B_hi][B_lo]
   __shared__ __align__(8) MtBars bars;
   __shared__ uint32_t tmem_slot;
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int NRAW = p.nraw;
+  const int tid = threadIdx.x, warp = ptx::uniform_warp_idx(), lane = tid & 31;
+  const int NST = p.nst;                                                    // 8 or 4 (a multiple of the 4 chunk owners)
   const int c_beg = (int)blockIdx.x * p.per;
   const int c_end = (c_beg + p.per < p.nch_total) ? (c_beg + p.per) : p.nch_total;
+  const int nloc = c_end - c_beg;
+  const int item0 = c_beg / p.nck, kc_first = c_beg - item0 * p.nck;       // the only runtime divisions: once per thread
+  const int nbuf = p.nbuf;
 
   if (tid == 0) {
-    for (int i = 0; i < kMtNST; ++i) { ptx::mbar_init(&bars.full[i], 4); ptx::mbar_init(&bars.empty[i], 1); }
-    for (int i = 0; i < NRAW; ++i) { ptx::mbar_init(&bars.raw_full[i], 1); ptx::mbar_init(&bars.raw_empty[i], 4); }
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&bars.acc_full[i], 1); ptx::mbar_init(&bars.acc_empty[i], 4); }
+    for (int i = 0; i < NST; ++i) { ptx::mbar_init(&bars.raw_full[i], 1); ptx::mbar_init(&bars.full[i], 4); ptx::mbar_init(&bars.empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&bars.acc_full[i], kMtNIssue); ptx::mbar_init(&bars.acc_empty[i], 4); }
     ptx::fence_mbar_init();
   }
-  if (warp == kMtMmaWarp) {
+  if (warp == kMtIssue0) {
     ptx::tmem_alloc(&tmem_slot, 512);
     ptx::tmem_relinquish();
   }
@@ -219,178 +278,223 @@ k_mix_tc(MtParams p, const __grid_constant__ CUtensorMap tmap_w, const __grid_co
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
-  // TMEM columns: accumulator a (0/1): high sum at a*2*npad, low sum at a*2*npad + npad; A stage s at 256 + 64*s:
-  // [Wr_hi 16][Wr_lo 16][Wi_hi 16][Wi_lo 16]
+  // TMEM columns: accumulator of issuer q in buffer a at (a * 4 + q) * npad (<= 256 in total); A_lo of stage s at 256 + 32*s
   const uint32_t ta0 = 256u;
 
-  if (warp < 8) {
-    // ================================================================== convert
-    const int grp = warp >> 2, cw = warp & 3;
+  if (warp < kMtCvtWarps) {
+    // ================================================================== convert: group q = chunks g = q (mod 4)
+    const int q = warp >> 2, cw = warp & 3;
     const int row = tid & 127;                                             // output channel within the tile = TMEM lane
-    for (int c = c_beg, g = 0; c < c_end; ++c, ++g) {
-      if ((g & 1) != grp) continue;
-      const int s = g % kMtNST, r = g % NRAW;
-      const int kc = c % p.nck;
-      if (g >= kMtNST) ptx::mbar_wait(&bars.empty[s], (uint32_t)(((g / kMtNST) - 1) & 1));
+    const uint32_t sw = (uint32_t)(row & 7);
+    const uint32_t trow0 = tmem_base + ((uint32_t)(cw * 32) << 16) + ta0;
+    const int ii = row & 15, bb0 = row >> 4;                               // this thread's spectrum elements: (bb0 + 8 t, ii)
+    // Bx element (n, k = 2 ii + ri) at (k/4)*lbo + (n/8)*128 + (n%8)*16 + (k%4)*4; rows n = 2 bb, 2 bb + 1 share an 8-row group
+    const uint32_t kof = (uint32_t)(ii >> 1) * lbo + (uint32_t)(ii & 1) * 8u;
+    int s = q;                                                             // ring stage of chunk g = q, q + 4, ...
+    uint32_t ph = 0;                                                       // parity of raw_full[s]
+    int kc = kc_first + q;
+    while (kc >= p.nck) kc -= p.nck;
+    for (int g = q; g < nloc; g += 4) {
+      if (cw == 0 && lane == 0) MT_TRACE(1, g, 0);
+      ptx::mbar_wait(&bars.raw_full[s], ph);                                // (the producer already waited for empty[s])
+      if (cw == 0 && lane == 0) MT_TRACE(1, g, 1);
       ptx::tc_fence_after();
-      ptx::mbar_wait(&bars.raw_full[r], (uint32_t)((g / NRAW) & 1));
-      const unsigned char* slot = sRaw + (size_t)r * raw_slot;
-      // ---- weights: this thread's 128-byte row (16 complex), 128-byte swizzle: chunk j sits at j ^ (row & 7)
-      uint32_t rh[16], rl[16], ih[16], il[16];
-      {
-        const unsigned char* wrow = slot + (uint32_t)row * 128u;
-        const uint32_t sw = (uint32_t)(row & 7);
+      unsigned char* st = base + (uint32_t)s * stage_bytes;
+      if (!MT_DBG(4)) {
+        // ---- A_lo = W - trunc(W): this thread's 128-byte row (k = 0..31), 128-byte swizzle: chunk j sits at j ^ (row & 7)
+        const unsigned char* wrow = st + (uint32_t)row * 128u;
+        const uint32_t trow = trow0 + (uint32_t)s * 32u;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 v = *reinterpret_cast<const float4*>(wrow + (((uint32_t)j ^ sw) << 4));   // (re, im) of i = 2j, 2j+1
-          float h;
-          h = mt_hi(v.x); rh[2 * j] = __float_as_uint(h); rl[2 * j] = __float_as_uint(v.x - h);
-          h = mt_hi(v.y); ih[2 * j] = __float_as_uint(h); il[2 * j] = __float_as_uint(v.y - h);
-          h = mt_hi(v.z); rh[2 * j + 1] = __float_as_uint(h); rl[2 * j + 1] = __float_as_uint(v.z - h);
-          h = mt_hi(v.w); ih[2 * j + 1] = __float_as_uint(h); il[2 * j + 1] = __float_as_uint(v.w - h);
+        for (int half = 0; half < 2; ++half) {
+          uint32_t lo[16];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 v = *reinterpret_cast<const float4*>(wrow + ((((uint32_t)(half * 4 + j)) ^ sw) << 4));
+            lo[4 * j + 0] = __float_as_uint(v.x - mt_hi(v.x));
+            lo[4 * j + 1] = __float_as_uint(v.y - mt_hi(v.y));
+            lo[4 * j + 2] = __float_as_uint(v.z - mt_hi(v.z));
+            lo[4 * j + 3] = __float_as_uint(v.w - mt_hi(v.w));
+          }
+          ptx::tmem_st16(trow + (uint32_t)half * 16u, lo);
         }
-      }
-      const uint32_t trow = tmem_base + ((uint32_t)(cw * 32) << 16) + ta0 + (uint32_t)s * 64u;
-      ptx::tmem_st16(trow, rh);
-      ptx::tmem_st16(trow + 16u, rl);
-      ptx::tmem_st16(trow + 32u, ih);
-      ptx::tmem_st16(trow + 48u, il);
-      // ---- spectrum rows -> canonical K-major B blocks: element (n, kk) at (kk/4)*lbo + (n/8)*128 + (n%8)*16 + (kk%4)*4
-      {
-        const unsigned char* xraw = slot + w_slot;
-        unsigned char* sb = sB + (size_t)s * b_stage;
-        const int i0 = kc * kMtBK;
-        for (int e = row; e < p.bp * kMtBK; e += 128) {
-          const int bb = e >> 4, kk = e & 15;
-          float2 x = *reinterpret_cast<const float2*>(xraw + (uint32_t)bb * 128u + (uint32_t)kk * 8u);
-          if (bb >= p.B || i0 + kk >= p.Cin) x = make_float2(0.f, 0.f);
-          const float xr_h = mt_hi(x.x), xi_h = mt_hi(x.y);
-          const float xr_l = x.x - xr_h, xi_l = x.y - xi_h;
-          const int n0 = 2 * bb, n1 = n0 + 1;
-          const uint32_t kof = (uint32_t)(kk >> 2) * lbo + (uint32_t)(kk & 3) * 4u;
+        // ---- spectrum rows -> Bx_hi (raw values: the tensor core truncates) and Bx_lo, canonical K-major blocks
+        const unsigned char* xraw = st + x_off;
+        unsigned char* sb = st + b_off;
+        const bool kvalid = kc * kMtBK + ii < p.Cin;
+        for (int bb = bb0; bb < p.bp; bb += 8) {
+          float2 x = *reinterpret_cast<const float2*>(xraw + (uint32_t)bb * 128u + (uint32_t)ii * 8u);
+          if (bb >= p.B || !kvalid) x = make_float2(0.f, 0.f);
+          const float xr_l = x.x - mt_hi(x.x), xi_l = x.y - mt_hi(x.y);
+          const int n0 = 2 * bb;
           const uint32_t o0f = kof + (uint32_t)(n0 >> 3) * 128u + (uint32_t)(n0 & 7) * 16u;
-          const uint32_t o1f = kof + (uint32_t)(n1 >> 3) * 128u + (uint32_t)(n1 & 7) * 16u;
-          *reinterpret_cast<float*>(sb + o0f) = xr_h;                        // XA: (re | im)
-          *reinterpret_cast<float*>(sb + o1f) = xi_h;
-          *reinterpret_cast<float*>(sb + blk + o0f) = xr_l;
-          *reinterpret_cast<float*>(sb + blk + o1f) = xi_l;
-          *reinterpret_cast<float*>(sb + 2 * blk + o0f) = -xi_h;             // XB: (-im | re)
-          *reinterpret_cast<float*>(sb + 2 * blk + o1f) = xr_h;
-          *reinterpret_cast<float*>(sb + 3 * blk + o0f) = -xi_l;
-          *reinterpret_cast<float*>(sb + 3 * blk + o1f) = xr_l;
+          *reinterpret_cast<float2*>(sb + o0f) = make_float2(x.x, -x.y);            // row (b, re): (Xr, -Xi)
+          *reinterpret_cast<float2*>(sb + o0f + 16u) = make_float2(x.y, x.x);       // row (b, im): (Xi,  Xr)
+          *reinterpret_cast<float2*>(sb + blk + o0f) = make_float2(xr_l, -xi_l);
+          *reinterpret_cast<float2*>(sb + blk + o0f + 16u) = make_float2(xi_l, xr_l);
         }
       }
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&bars.raw_empty[r]);                   // raw slot fully consumed
       ptx::tmem_st_wait();
       ptx::tc_fence_before();
-      ptx::fence_proxy_async();                                              // the B blocks went through st.shared
+      ptx::fence_proxy_async();                                              // the Bx blocks went through st.shared
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&bars.full[s]);
+      if (cw == 0 && lane == 0) MT_TRACE(1, g, 3);
+      s += 4; if (s >= NST) { s -= NST; ph ^= 1u; }
+      kc += 4; while (kc >= p.nck) kc -= p.nck;
     }
-  } else if (warp == kMtMmaWarp) {
-    if (lane == 0) {
-      // ================================================================ MMA issue
+  } else if (warp >= kMtIssue0 && warp < kMtIssue0 + kMtNIssue) {
+    {
+      // ================================================================ MMA issue: issuer q = chunks g = q (mod 4), accumulator q
+      // (the whole warp runs this loop converged with warp-uniform values; one elected lane issues, see pdes_ptx.cuh)
+      const int q = warp - kMtIssue0;
       const uint32_t idesc = ptx::idesc_tf32(128, npad);
-      const uint64_t bd0 = ptx::smem_desc_noswizzle(ptx::smem_u32(sB), lbo, 128);
-      uint32_t part = 0;
+      const uint32_t sbase = ptx::smem_u32(base);
+      const uint64_t kstepb = (uint64_t)((2u * lbo) >> 4);                   // B: 8 k = two k-quads
+      int kc = kc_first + q, part = 0;
+      while (kc >= p.nck) { kc -= p.nck; ++part; }
+      int s = q;
+      uint32_t fph = 0;
+      int done_part = 0;                                                     // parts whose acc_full this issuer has committed
       bool fresh = true;
-      for (int c = c_beg, g = 0; c < c_end; ++c, ++g) {
-        const int s = g % kMtNST;
-        const int kc = c % p.nck;
-        const uint32_t a = part & 1u;
-        if (fresh) {
-          if (part >= 2) ptx::mbar_wait(&bars.acc_empty[a], ((part >> 1) - 1) & 1u);
-          ptx::tc_fence_after();
-        }
-        ptx::mbar_wait(&bars.full[s], (uint32_t)((g / kMtNST) & 1));
-        ptx::tc_fence_after();
-        const uint32_t d_hi = tmem_base + a * 2u * (uint32_t)npad, d_lo = d_hi + (uint32_t)npad;
-        const uint32_t ta = tmem_base + ta0 + (uint32_t)s * 64u;
-        const uint64_t sd = (uint64_t)(((uint32_t)s * b_stage) >> 4);
-#pragma unroll
-        for (int ks = 0; ks < 2; ++ks) {
-          const uint64_t kb = sd + (uint64_t)((ks * 2 * lbo) >> 4);
-          const uint64_t xa_hi = bd0 + kb, xa_lo = bd0 + kb + (blk >> 4), xb_hi = bd0 + kb + ((2 * blk) >> 4),
-                         xb_lo = bd0 + kb + ((3 * blk) >> 4);
-          const uint32_t wr_hi = ta + ks * 8, wr_lo = ta + 16 + ks * 8, wi_hi = ta + 32 + ks * 8, wi_lo = ta + 48 + ks * 8;
-          const uint32_t acc0 = (fresh && ks == 0) ? 0u : 1u;
-          ptx::mma_tf32_ta(d_lo, wr_lo, xa_hi, idesc, acc0);                 // cross terms -> low accumulator
-          ptx::mma_tf32_ta(d_lo, wr_hi, xa_lo, idesc, 1u);
-          ptx::mma_tf32_ta(d_lo, wi_lo, xb_hi, idesc, 1u);
-          ptx::mma_tf32_ta(d_lo, wi_hi, xb_lo, idesc, 1u);
-          ptx::mma_tf32_ta(d_hi, wr_hi, xa_hi, idesc, acc0);                 // hi*hi terms -> high accumulator
-          ptx::mma_tf32_ta(d_hi, wi_hi, xb_hi, idesc, 1u);
-        }
-        ptx::tc_commit(&bars.empty[s]);
-        fresh = false;
-        if (kc == p.nck - 1 || c + 1 == c_end) {                             // item (or this CTA's part of it) complete
-          ptx::tc_commit(&bars.acc_full[a]);
-          ++part;
+      for (int g = q; g < nloc; g += kMtNIssue) {
+        while (done_part < part) {                                           // close the parts that ended before this chunk
+          ptx::tc_commit_ws(&bars.acc_full[(nbuf == 2) ? (done_part & 1) : 0]);
+          ++done_part;
           fresh = true;
         }
+        const uint32_t a = (nbuf == 2) ? (uint32_t)(part & 1) : 0u;
+        if (fresh && part >= nbuf) {
+          ptx::mbar_wait(&bars.acc_empty[a], (uint32_t)((((nbuf == 2) ? (part >> 1) : part) - 1) & 1));
+          ptx::tc_fence_after();
+        }
+        if (q == 0 && lane == 0) MT_TRACE(2, g, 0);
+        ptx::mbar_wait(&bars.full[s], fph);
+        if (q == 0 && lane == 0) MT_TRACE(2, g, 1);
+        ptx::tc_fence_after();
+        const uint32_t dacc = tmem_base + (a * 4u + (uint32_t)q) * (uint32_t)npad;
+        const uint32_t sst = sbase + (uint32_t)s * stage_bytes;
+        const uint64_t a_hi = mt_desc_sw128(sst);                            // + 2 (= 32 bytes) per k-step of 8
+        const uint64_t b_hi = ptx::smem_desc_noswizzle(sst + b_off, lbo, 128), b_lo = b_hi + (uint64_t)(blk >> 4);
+        const uint32_t a_lo = tmem_base + ta0 + (uint32_t)s * 32u;
+        if (!MT_DBG(1)) {
+          ptx::mma_tf32_ws(dacc, a_hi, b_hi, idesc, fresh ? 0u : 1u);                           // hi * hi
+          ptx::mma_tf32_ws(dacc, a_hi + 2, b_hi + kstepb, idesc, 1u);
+          ptx::mma_tf32_ws(dacc, a_hi + 4, b_hi + 2 * kstepb, idesc, 1u);
+          ptx::mma_tf32_ws(dacc, a_hi + 6, b_hi + 3 * kstepb, idesc, 1u);
+          ptx::mma_tf32_ws(dacc, a_hi, b_lo, idesc, 1u);                                        // hi * lo
+          ptx::mma_tf32_ws(dacc, a_hi + 2, b_lo + kstepb, idesc, 1u);
+          ptx::mma_tf32_ws(dacc, a_hi + 4, b_lo + 2 * kstepb, idesc, 1u);
+          ptx::mma_tf32_ws(dacc, a_hi + 6, b_lo + 3 * kstepb, idesc, 1u);
+          ptx::mma_tf32_ta_ws(dacc, a_lo, b_hi, idesc, 1u);                                     // lo * hi
+          ptx::mma_tf32_ta_ws(dacc, a_lo + 8, b_hi + kstepb, idesc, 1u);
+          ptx::mma_tf32_ta_ws(dacc, a_lo + 16, b_hi + 2 * kstepb, idesc, 1u);
+          ptx::mma_tf32_ta_ws(dacc, a_lo + 24, b_hi + 3 * kstepb, idesc, 1u);
+        }
+        ptx::tc_commit_ws(&bars.empty[s]);
+        if (q == 0 && lane == 0) MT_TRACE(2, g, 2);
+        fresh = false;
+        s += 4; if (s >= NST) { s -= NST; fph ^= 1u; }
+        kc += kMtNIssue;
+        while (kc >= p.nck) { kc -= p.nck; ++part; }
+      }
+      int nparts = 1;                                                        // close the remaining parts of this CTA's range
+      { int e = p.nck - kc_first; while (e < nloc) { e += p.nck; ++nparts; } }
+      while (done_part < nparts) {
+        ptx::tc_commit_ws(&bars.acc_full[(nbuf == 2) ? (done_part & 1) : 0]);
+        ++done_part;
       }
     }
-  } else if (warp == kMtTmaWarp) {
-    if (lane == 0) {
-      // ================================================================ TMA producer
+  } else if (warp >= kMtTma0 && warp < kMtTma0 + 4) {
+    {
+      // ================================================================ TMA producers: producer q = chunks g = q (mod 4)
+      // (a single producer thread needs ~600 cycles per chunk -- wait, expect_tx, two TMA issues, counters -- and paced
+      // the whole kernel; four of them make the pipeline four independent lanes producer -> convert group -> issuer)
+      const int q = warp - kMtTma0;
       const uint32_t wbytes = (uint32_t)p.to * 128u, xbytes = (uint32_t)p.bp * 128u;
-      for (int c = c_beg, g = 0; c < c_end; ++c, ++g) {
-        const int r = g % NRAW;
-        if (g >= NRAW) ptx::mbar_wait(&bars.raw_empty[r], (uint32_t)(((g / NRAW) - 1) & 1));
-        const int item = c / p.nck, kc = c - item * p.nck;
-        const int m = item / p.ntile, t = item - m * p.ntile;
-        unsigned char* slot = sRaw + (size_t)r * raw_slot;
-        ptx::mbar_arrive_expect_tx(&bars.raw_full[r], wbytes + xbytes);
-        ptx::tma_load_3d(slot, &tmap_w, kc * 2 * kMtBK, t * p.to, m, &bars.raw_full[r]);
-        ptx::tma_load_2d(slot + w_slot, &tmap_x, kc * 2 * kMtBK, m * p.B, &bars.raw_full[r]);
+      int m = item0 / p.ntile, t = item0 - m * p.ntile, kc = kc_first + q;
+      while (kc >= p.nck) { kc -= p.nck; if (++t == p.ntile) { t = 0; ++m; } }
+      int s = q;
+      uint32_t eph = 1;                                                      // parity of empty[s] (first pass: no wait)
+      for (int g = q; g < nloc; g += 4) {
+        if (q == 0 && lane == 0) MT_TRACE(0, g, 0);
+        if (g >= NST) ptx::mbar_wait(&bars.empty[s], eph);
+        if (q == 0 && lane == 0) MT_TRACE(0, g, 1);
+        unsigned char* st = base + (uint32_t)s * stage_bytes;
+        if (MT_DBG(2)) {
+          ptx::mbar_arrive_ws(&bars.raw_full[s]);
+        } else {
+          ptx::mbar_arrive_expect_tx_ws(&bars.raw_full[s], wbytes + xbytes);
+          ptx::tma_load_2d_ws(st, &tmap_w, 0, (c_beg + g) * p.to, &bars.raw_full[s]);       // chunk c = one contiguous block
+          ptx::tma_load_2d_ws(st + x_off, &tmap_x, kc * 2 * kMtBK, m * p.B, &bars.raw_full[s]);
+        }
+        if (q == 0 && lane == 0) MT_TRACE(0, g, 2);
+        s += 4; if (s >= NST) { s -= NST; eph ^= 1u; }
+        kc += 4;
+        while (kc >= p.nck) { kc -= p.nck; if (++t == p.ntile) { t = 0; ++m; } }
       }
     }
-  } else if (warp >= 8 && warp < 12) {
+  } else if (warp >= kMtEpi0 && warp < kMtEpi0 + 4) {
     // ==================================================================== epilogue: lane = output channel
     const int quad = warp & 3;
     const int rowl = quad * 32 + lane;
     const size_t pstride = (size_t)p.nmodes * p.B * p.Cout;
     uint32_t part = 0;
+    int m = item0 / p.ntile, t = item0 - m * p.ntile, kc0 = kc_first;
     for (int c = c_beg; c < c_end;) {
-      const int item = c / p.nck, kc0 = c - item * p.nck;
-      int cl = (item + 1) * p.nck;                                           // end of this part
+      int cl = c + (p.nck - kc0);                                            // end of this part
       if (cl > c_end) cl = c_end;
-      const int m = item / p.ntile, t = item - m * p.ntile;
       const int o = t * p.to + rowl;
       const bool valid = rowl < p.to && o < p.Cout;
-      const uint32_t a = part & 1u;
-      ptx::mbar_wait(&bars.acc_full[a], (part >> 1) & 1u);
+      const uint32_t a = (nbuf == 2) ? (part & 1u) : 0u;
+      ptx::mbar_wait(&bars.acc_full[a], ((nbuf == 2) ? (part >> 1) : part) & 1u);
       ptx::tc_fence_after();
-      const uint32_t tb = tmem_base + ((uint32_t)(quad * 32) << 16) + a * 2u * (uint32_t)npad;
+      const uint32_t tb = tmem_base + ((uint32_t)(quad * 32) << 16) + a * 4u * (uint32_t)npad;
       float2* dst = p.O2 + (kc0 != 0 ? pstride : 0) + ((size_t)m * p.B) * p.Cout + o;   // partial 1 = continuation of a split item
+      // accumulator q received the chunks g = q (mod 4) of this part; a part shorter than 4 chunks leaves some untouched
+      const int g0 = c - c_beg, nch_part = cl - c;
+      bool used[4];
+#pragma unroll
+      for (int qq = 0; qq < 4; ++qq) used[qq] = nch_part >= 4 || (((qq - g0) & 3) < nch_part);
       for (int n0 = 0; n0 < npad; n0 += 8) {
-        uint32_t vh[8], vl[8];
-        ptx::tmem_ld8(tb + (uint32_t)n0, vh);
-        ptx::tmem_ld8(tb + (uint32_t)(npad + n0), vl);
+        uint32_t v0[8], v1[8], v2[8], v3[8];
+        ptx::tmem_ld8(tb + (uint32_t)n0, v0);
+        ptx::tmem_ld8(tb + (uint32_t)(npad + n0), v1);
+        ptx::tmem_ld8(tb + (uint32_t)(2 * npad + n0), v2);
+        ptx::tmem_ld8(tb + (uint32_t)(3 * npad + n0), v3);
         ptx::tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          if (!used[0]) v0[e] = 0u;
+          if (!used[1]) v1[e] = 0u;
+          if (!used[2]) v2[e] = 0u;
+          if (!used[3]) v3[e] = 0u;
+        }
         if (n0 + 8 >= npad) {                                                // accumulators fully read: hand them back
           ptx::tc_fence_before();
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(&bars.acc_empty[a]);
         }
-        if (valid) {
+        if (valid && !MT_DBG(8)) {
 #pragma unroll
           for (int e = 0; e < 8; e += 2) {
             const int bb = (n0 + e) >> 1;
-            if (bb < p.B)
-              dst[(size_t)bb * p.Cout] = make_float2(__uint_as_float(vh[e]) + __uint_as_float(vl[e]),
-                                                     __uint_as_float(vh[e + 1]) + __uint_as_float(vl[e + 1]));
+            if (bb < p.B) {
+              const float re = (__uint_as_float(v2[e]) + __uint_as_float(v3[e])) + (__uint_as_float(v1[e]) + __uint_as_float(v0[e]));
+              const float im = (__uint_as_float(v2[e + 1]) + __uint_as_float(v3[e + 1])) + (__uint_as_float(v1[e + 1]) + __uint_as_float(v0[e + 1]));
+              dst[(size_t)bb * p.Cout] = make_float2(re, im);
+            }
           }
         }
       }
       ++part;
       c = cl;
+      kc0 = 0;
+      if (++t == p.ntile) { t = 0; ++m; }
     }
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == kMtMmaWarp) {
+  if (warp == kMtIssue0) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, 512);
   }
@@ -439,6 +543,10 @@ inline int mt_sms() {
 
 extern "C" {
 
+#if defined(PDES_MT_ABLATE) && !defined(PDES_CPU_EMU)
+int pdes_mt_trace_read(long long* host) { return (int)cudaMemcpyFromSymbol(host, pdes::g_mt_trace, sizeof(long long) * 3 * 64 * 4); }
+#endif
+
 /* 1 when the tensor-core K2 covers the shape: 2B (padded to 16) <= 64 and the tensor-core mode is on. */
 int pdes_mix_tc_ok(int B, int Cin, int Cout, int m1, int m2) {
 #ifdef PDES_CPU_EMU
@@ -455,7 +563,7 @@ int pdes_mix_tc_ok(int B, int Cin, int Cout, int m1, int m2) {
 
 size_t pdes_mix_tc_pack_floats(int Cin, int Cout, int m1, int m2) {
   if (Cin <= 0 || Cout <= 0 || m1 <= 0 || m2 <= 0) return 0;
-  return (size_t)2 * m1 * m2 * Cout * pdes::mt_cinp(Cin) * 2;
+  return (size_t)2 * m1 * m2 * pdes::mt_ntile(Cout) * pdes::mt_to(Cout) * pdes::mt_cinp(Cin) * 2;
 }
 
 size_t pdes_mix_tc_x2_floats(int B, int Cin, int m1, int m2) {
@@ -473,12 +581,12 @@ int pdes_mix_tc_pack(const float* w1, const float* w2, float* Wp, int Cin, int C
   using namespace pdes;
   PDES_REQUIRE(w1 && w2 && Wp, PDES_ERR_ARG, "pdes_mix_tc_pack: null pointer");
   PDES_REQUIRE(Cin > 0 && Cout > 0 && m1 > 0 && m2 > 0 && H > 0 && m1 <= H, PDES_ERR_ARG, "pdes_mix_tc_pack: bad sizes");
-  const int CinP = mt_cinp(Cin), MM = m1 * m2;
+  const int CinP = mt_cinp(Cin), MM = m1 * m2, ntile = mt_ntile(Cout), to = mt_to(Cout);
   PDES_REQUIRE(Cout <= 65535, PDES_ERR_UNSUPPORTED, "pdes_mix_tc_pack: too many output channels");
   auto kfn = k_mix_tc_pack;
-  const dim3 grid((unsigned)Cout, (unsigned)ceil_div(CinP, 32), (unsigned)(2 * ceil_div(MM, 32)));
+  const dim3 grid((unsigned)(ntile * to), (unsigned)ceil_div(CinP, 32), (unsigned)(2 * ceil_div(MM, 32)));
   PDES_LAUNCH(kfn, grid, dim3(256), 0, stream, reinterpret_cast<const float2*>(w1), reinterpret_cast<const float2*>(w2),
-              reinterpret_cast<float2*>(Wp), Cin, Cout, CinP, m1, m2, H);
+              reinterpret_cast<float2*>(Wp), Cin, Cout, CinP, m1, m2, H, ntile, to);
   return check_launch("pdes_mix_tc_pack");
 }
 
@@ -500,11 +608,11 @@ int pdes_mix_tc_fwd(const float* X2, const float* Wp, float* O2, int B, int Cin,
   memset(&tx, 0, sizeof(tx));
   const int nmodes = 2 * m1 * m2;
   {
-    const cuuint64_t gdim[3] = {(cuuint64_t)g.CinP * 2, (cuuint64_t)Cout, (cuuint64_t)nmodes};
-    const cuuint64_t gstr[2] = {(cuuint64_t)g.CinP * 8, (cuuint64_t)g.CinP * 8 * (cuuint64_t)Cout};
-    const cuuint32_t box[3] = {32, (cuuint32_t)g.to, 1};
-    const cuuint32_t estr[3] = {1, 1, 1};
-    const CUresult r = enc(&tw, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(Wp), gdim, gstr, box, estr,
+    const cuuint64_t gdim[2] = {32, (cuuint64_t)g.nch * (cuuint64_t)g.to};      // [chunk][row][16 i x (re,im)]: rows of 128 bytes
+    const cuuint64_t gstr[1] = {128};
+    const cuuint32_t box[2] = {32, (cuuint32_t)g.to};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = enc(&tw, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(Wp), gdim, gstr, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     PDES_REQUIRE(r == CUDA_SUCCESS, PDES_ERR_UNSUPPORTED, "pdes_mix_tc_fwd: cuTensorMapEncodeTiled(Wp) failed (%d)", (int)r);
@@ -523,14 +631,18 @@ int pdes_mix_tc_fwd(const float* X2, const float* Wp, float* O2, int B, int Cin,
   p.O2 = reinterpret_cast<float2*>(O2);
   p.B = B; p.Cin = Cin; p.Cout = Cout; p.CinP = g.CinP; p.nmodes = nmodes; p.npad = g.npad; p.bp = g.bp;
   p.ntile = g.ntile; p.to = g.to; p.nck = g.nck; p.per = g.per; p.nch_total = g.nch;
-  const size_t raw_slot = 128 * 128 + (((size_t)g.bp * 128 + 1023) & ~size_t(1023));
+  p.nbuf = (8 * g.npad <= 256) ? 2 : 1;                                    // double-buffered accumulators when they fit
+  p.dbg = 0;
+#ifdef PDES_MT_ABLATE
+  if (const char* e = getenv("PDES_MT_DBG")) p.dbg = atoi(e);
+#endif
   const size_t lbo = (size_t)(g.npad / 8) * 128 + 16;
-  const size_t fixed = (size_t)kMtNST * 16 * lbo + 2048;
-  int nraw = (int)((226 * 1024 - fixed) / raw_slot);
-  if (nraw > kMtMaxRaw) nraw = kMtMaxRaw;
-  PDES_REQUIRE(nraw >= 2, PDES_ERR_UNSUPPORTED, "pdes_mix_tc_fwd: not enough shared memory");
-  p.nraw = nraw;
-  const size_t smem = (size_t)nraw * raw_slot + (size_t)kMtNST * 16 * lbo + 1024;
+  const size_t x_off = 128 * 128, b_off = x_off + (((size_t)g.bp * 128 + 127) & ~size_t(127));
+  const size_t stage_bytes = (b_off + 2 * 8 * lbo + 1023) & ~size_t(1023);
+  p.stage_bytes = (uint32_t)stage_bytes; p.x_off = (uint32_t)x_off; p.b_off = (uint32_t)b_off;
+  p.nst = (kMtMaxStages * stage_bytes + 2048 <= 227 * 1024) ? kMtMaxStages : 4;
+  PDES_REQUIRE((size_t)p.nst * stage_bytes + 2048 <= 227 * 1024, PDES_ERR_UNSUPPORTED, "pdes_mix_tc_fwd: not enough shared memory");
+  const size_t smem = (size_t)p.nst * stage_bytes + 1024;
   auto kfn = k_mix_tc;
   PDES_SET_SMEM(kfn, smem);
   PDES_LAUNCH(kfn, dim3((unsigned)g.G), dim3(kMtThreads), smem, stream, p, tw, tx);
@@ -549,11 +661,16 @@ int pdes_inv_h_modes(const float* O2, int B, int Cin, int C, int H, int m1, int 
   const MtGeom g = mt_geom(B, Cin, C, m1, m2, mt_sms());
   SplitRule rule;
   rule.nck = g.nck; rule.per = g.per; rule.ntile = g.ntile; rule.to = g.to;
-  const size_t smem = ((size_t)2 * m1 * 32 + (size_t)(H / 2 + 1) * 2 * m1) * sizeof(float2);
-  PDES_REQUIRE(smem <= (size_t)kMaxDynSmem, PDES_ERR_UNSUPPORTED, "pdes_inv_h_modes: needs %zu B of shared memory", smem);
+  const int npair = H / 2 + 1, npp = ceil_div(npair, kIh2HP) * kIh2HP;
+  const size_t smem = ((size_t)2 * (m1 + 1) * 32 + (size_t)(m1 + 1) * npp) * sizeof(float2);
+  PDES_REQUIRE(smem <= (size_t)kMaxDynSmem && (long)H * m1 < (1L << 31), PDES_ERR_UNSUPPORTED,
+               "pdes_inv_h_modes: needs %zu B of shared memory", smem);
+  int nwarp = ceil_div(npair, kIh2HP);
+  if (nwarp > kIh2MaxWarps) nwarp = kIh2MaxWarps;
   auto kfn = k_inv_h2;
   if (smem > 48 * 1024) PDES_SET_SMEM(kfn, smem);
-  PDES_LAUNCH(kfn, dim3((unsigned)ceil_div(C, 32), (unsigned)m2, (unsigned)B), dim3(kIh2Threads), smem, stream,
+  PDES_MAX_CARVEOUT(kfn);
+  PDES_LAUNCH(kfn, dim3((unsigned)ceil_div(C, 32), (unsigned)m2, (unsigned)B), dim3((unsigned)(32 * nwarp)), smem, stream,
               reinterpret_cast<const float2*>(O2), rule, B, C, H, m1, m2, tables /* twh [H][2] sits at offset 0 of the blob */, Z);
   return check_launch("pdes_inv_h_modes");
 }

@@ -103,12 +103,14 @@ def check_spectral_tc(be, shape, run_mma):
     w1, w2 = _weights(rng, Cin, Cout, m1, m2)
     dw1, dw2 = be.upload(w1), be.upload(w2)
     # ---- packed master copy: Wp[m][o][i_pad] complex, dead rows and pad columns zero
-    assert lib.pdes_mix_tc_pack_floats(Cin, Cout, m1, m2) == MM2 * Cout * CinP * 2
-    Wp = be.empty((MM2, Cout, CinP), complex_=True)
+    ntile, to, nck = g["ntile"], g["to"], g["nck"]
+    assert lib.pdes_mix_tc_pack_floats(Cin, Cout, m1, m2) == MM2 * ntile * to * CinP * 2
+    Wp = be.empty((MM2, ntile, nck, to, 16), complex_=True)               # [m][tile][chunk][row][16 i]
     be.check(lib.pdes_mix_tc_pack(be.ptr(dw1), be.ptr(dw2), be.ptr(Wp), Cin, Cout, H, m1, m2, be.stream))
     wt = np.concatenate([w1, w2], axis=2) * so.live_rows(H, m1)[None, None, :, None]        # [Cin, Cout, 2m1, m2]
-    ref_wp = np.zeros((MM2, Cout, CinP), dtype=np.complex64)
-    ref_wp[:, :, :Cin] = wt.reshape(Cin, Cout, MM2).transpose(2, 1, 0)
+    full = np.zeros((MM2, ntile * to, CinP), dtype=np.complex64)          # [m][o padded][i padded]
+    full[:, :Cout, :Cin] = wt.reshape(Cin, Cout, MM2).transpose(2, 1, 0)
+    ref_wp = full.reshape(MM2, ntile, to, nck, 16).transpose(0, 1, 3, 2, 4)
     assert np.array_equal(be.download(Wp), ref_wp), f"weight pack {shape}"
     # ---- K1 with the mode-major copy
     x0 = rng.standard_normal((B, C0, H, W)).astype(np.float32)

@@ -4,7 +4,7 @@ import numpy as np
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from neural_pde_surrogates_b200 import _native
-lib = _native.library()
+lib = _native.bind(ctypes.CDLL(os.environ['PDES_LIB'])) if os.environ.get('PDES_LIB') else _native.library()
 dev = torch.device("cuda:0")
 B = 16
 C0, C1, Cout, H, W, m1, m2 = 192, 1, 192, 96, 64, 10, 10

@@ -7,7 +7,7 @@
 #include "pdes_ptx.cuh"
 using namespace pdes;
 
-__global__ void __launch_bounds__(128, 1) k(int N, int a_tmem, int nper, int niter, long long* cycles) {
+__global__ void __launch_bounds__(128, 1) k(int N, int a_tmem, int nper, int niter, long long* cycles, int nacc = 1, int na = 1) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ __align__(8) unsigned long long bar;
   __shared__ uint32_t slot;
@@ -28,7 +28,7 @@ __global__ void __launch_bounds__(128, 1) k(int N, int a_tmem, int nper, int nit
     const long long t0 = clock64();
     for (int it = 0; it < niter; ++it) {
       for (int j = 0; j < nper; ++j) {
-        if (a_tmem) ptx::mma_tf32_ta(tm, tm + 480, db, idesc, 1u);
+        if (a_tmem) ptx::mma_tf32_ta(tm + (uint32_t)((j % nacc) * N), tm + 448 + (uint32_t)((j % na) * 8), db, idesc, 1u);
         else ptx::mma_tf32(tm, da, db, idesc, 1u);
       }
       ptx::tc_commit(&bar);
@@ -47,7 +47,7 @@ int main() {
   long long* d; cudaMalloc(&d, 8);
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
   for (int a_tmem = 0; a_tmem < 2; ++a_tmem)
-    for (int N : {64, 128, 192, 208, 256})
+    for (int N : {16, 32, 64, 128, 192, 208, 256})
       for (int nper : {6, 96}) {
         const int niter = 2000 / nper + 1;
         k<<<148, 128, 64 * 1024>>>(N, a_tmem, nper, niter, d);
@@ -55,6 +55,16 @@ int main() {
         const double per = (double)c / (niter * nper);
         printf("A from %s  N=%3d  %2d MMAs per commit+wait: %7.1f cycles/MMA  -> %6.0f MAC/clk/SM (%s)\n", a_tmem ? "TMEM" : "smem",
                N, nper, per, 128.0 * N * 8 / per, cudaGetErrorString(cudaGetLastError()));
+      }
+  // independent accumulators / A operands: is the ~100-cycle minimum a dependency through the accumulator?
+  for (int N : {32, 64})
+    for (int nacc : {1, 2, 4})
+      for (int na : {1, 4}) {
+        const int nper = 96, niter = 21;
+        k<<<148, 128, 64 * 1024>>>(N, 1, nper, niter, d, nacc, na);
+        long long c = 0; cudaMemcpy(&c, d, 8, cudaMemcpyDeviceToHost);
+        printf("A from TMEM  N=%3d  %d accumulators, %d A operands round-robin: %7.1f cycles/MMA (%s)\n", N, nacc, na,
+               (double)c / (niter * nper), cudaGetErrorString(cudaGetLastError()));
       }
   return 0;
 }
