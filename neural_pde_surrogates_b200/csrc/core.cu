@@ -76,6 +76,13 @@ int pdes_tables_fill(int H, int W, int m1, int m2, float* buf) {
     buf[t.twh + 2 * j] = (float)std::cos(a);
     buf[t.twh + 2 * j + 1] = (float)std::sin(a);
   }
+  for (int j = 0; j <= m1; ++j)
+    for (int pp = 0; pp < t.npp; ++pp) {
+      const long r = ((long)j * (long)(pp <= H / 2 ? pp : 0)) % (long)H;
+      const double a = two_pi * (double)r / (double)H;
+      buf[t.twp + ((size_t)j * t.npp + pp) * 2] = (float)std::cos(a);
+      buf[t.twp + ((size_t)j * t.npp + pp) * 2 + 1] = (float)std::sin(a);
+    }
   for (int l = 0; l < m2; ++l) {
     double c = 2.0;
     if (l == 0) c = 1.0;

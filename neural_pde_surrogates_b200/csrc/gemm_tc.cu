@@ -375,7 +375,9 @@ k_inv_w_gemm_tc_v3(TcParams p, int B, int ntiles_per_img, const __grid_constant_
   __shared__ __align__(8) V3RingBars bars;
   __shared__ uint32_t tmem_slot;
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // warp index as a warp-uniform value: the single-issuer roles below run with the whole warp converged and one elected
+  // lane issuing (ptx::*_ws), which keeps their operands in uniform registers (no waterfall loop per tcgen05 / TMA issue)
+  const int tid = threadIdx.x, warp = ptx::uniform_warp_idx(), lane = tid & 31;
   const int HW = p.H * p.W, W = p.W, J = 2 * p.m2;
   const int nx = tc_nchunks(p.K);
   const int ntiles = B * ntiles_per_img;
@@ -537,8 +539,8 @@ k_inv_w_gemm_tc_v3(TcParams p, int B, int ntiles_per_img, const __grid_constant_
       }
     }
   } else if (warp == kK3MmaWarp) {
-    if (lane == 0) {
-      // ================================================================ MMA issue
+    {
+      // ================================================================ MMA issue (warp-converged, one elected lane issues)
       const uint32_t idesc = ptx::idesc_tf32(kTcM, npad);
       const uint32_t lbo_a = (kTcM / 8) * 128, lbo_b = (uint32_t)(npad / 8) * 128, sbo = 128;
       const uint64_t a_hi0 = ptx::smem_desc_noswizzle(ptx::smem_u32(sA), lbo_a, sbo);
@@ -574,35 +576,35 @@ k_inv_w_gemm_tc_v3(TcParams p, int B, int ntiles_per_img, const __grid_constant_
             } else if constexpr (kTA) {
               const uint32_t ta = tmem_base + s * kTcBK + ks * 8;
               if (p.single_pass) {
-                ptx::mma_tf32_ta(dcol, ta + ta_hi, b_hi0 + kb, idesc, (c | ks) != 0 ? 1u : 0u);
+                ptx::mma_tf32_ta_ws(dcol, ta + ta_hi, b_hi0 + kb, idesc, (c | ks) != 0 ? 1u : 0u);
               } else {
-                ptx::mma_tf32_ta(dcol, ta + ta_lo, b_hi0 + kb, idesc, (c | ks) != 0 ? 1u : 0u);
+                ptx::mma_tf32_ta_ws(dcol, ta + ta_lo, b_hi0 + kb, idesc, (c | ks) != 0 ? 1u : 0u);
                 TRACE2(g * 10 + 3 + ks * 3);
-                ptx::mma_tf32_ta(dcol, ta + ta_hi, b_lo0 + kb, idesc, 1u);
+                ptx::mma_tf32_ta_ws(dcol, ta + ta_hi, b_lo0 + kb, idesc, 1u);
                 TRACE2(g * 10 + 4 + ks * 3);
-                ptx::mma_tf32_ta(dcol, ta + ta_hi, b_hi0 + kb, idesc, 1u);
+                ptx::mma_tf32_ta_ws(dcol, ta + ta_hi, b_hi0 + kb, idesc, 1u);
                 TRACE2(g * 10 + 5 + ks * 3);
               }
             } else if (p.single_pass) {
-              ptx::mma_tf32(dcol, a_hi0 + ka, b_hi0 + kb, idesc, (c | ks) != 0 ? 1u : 0u);
+              ptx::mma_tf32_ws(dcol, a_hi0 + ka, b_hi0 + kb, idesc, (c | ks) != 0 ? 1u : 0u);
             } else {
-              ptx::mma_tf32(dcol, a_lo0 + ka, b_hi0 + kb, idesc, (c | ks) != 0 ? 1u : 0u);
-              ptx::mma_tf32(dcol, a_hi0 + ka, b_lo0 + kb, idesc, 1u);
-              ptx::mma_tf32(dcol, a_hi0 + ka, b_hi0 + kb, idesc, 1u);
+              ptx::mma_tf32_ws(dcol, a_lo0 + ka, b_hi0 + kb, idesc, (c | ks) != 0 ? 1u : 0u);
+              ptx::mma_tf32_ws(dcol, a_hi0 + ka, b_lo0 + kb, idesc, 1u);
+              ptx::mma_tf32_ws(dcol, a_hi0 + ka, b_hi0 + kb, idesc, 1u);
             }
           }
-          if (dbg & 16) ptx::mbar_arrive(&bars.empty[s]); else
-          ptx::tc_commit(&bars.empty[s]);
+          if (dbg & 16) ptx::mbar_arrive_ws(&bars.empty[s]); else
+          ptx::tc_commit_ws(&bars.empty[s]);
           TRACE(1 * 512 + g * 4 + 3);
           TRACE2(g * 10 + 9);
           if (++s == (uint32_t)NST) { s = 0; sph ^= 1; }
         }
-        ptx::tc_commit(&bars.acc_full[a]);
+        ptx::tc_commit_ws(&bars.acc_full[a]);
       }
     }
   } else if (warp == kK3RawWarp) {
-    if (lane == 0) {
-      // ================================================================ raw ring issue (activation rows / Z rows)
+    {
+      // ================================================================ raw ring issue (warp-converged) (activation rows / Z rows)
       // The activations come from HBM (not L2): at ~1.2 us loaded latency a 3-slot ring (24 KB in flight per SM) paced
       // the whole kernel at ~1250 cycles per chunk; the ring is now as deep as shared memory allows (up to 8 slots).
       uint32_t g = 0, r = 0, rph = 1;
@@ -618,8 +620,8 @@ k_inv_w_gemm_tc_v3(TcParams p, int B, int ntiles_per_img, const __grid_constant_
           if (c < nsp) {
             // 16 consecutive (row, j) lines of Z are contiguous in memory: ONE bulk copy per spectral chunk
             const int nk = (kspec - c * kTcBK < kTcBK) ? (kspec - c * kTcBK) : kTcBK;
-            ptx::mbar_arrive_expect_tx(&bars.raw_full[r], (uint32_t)nk * p.N * 4);
-            ptx::bulk_g2s(dst, p.Z + (((size_t)b * p.H + h0) * J + (size_t)c * kTcBK) * p.N, (uint32_t)nk * p.N * 4,
+            ptx::mbar_arrive_expect_tx_ws(&bars.raw_full[r], (uint32_t)nk * p.N * 4);
+            ptx::bulk_g2s_ws(dst, p.Z + (((size_t)b * p.H + h0) * J + (size_t)c * kTcBK) * p.N, (uint32_t)nk * p.N * 4,
                           &bars.raw_full[r]);
           } else {
             const int cx = c - nsp;
@@ -627,17 +629,17 @@ k_inv_w_gemm_tc_v3(TcParams p, int B, int ntiles_per_img, const __grid_constant_
             if (cx < ntmap_chunks) {
               // one 2-D TMA box: 16 channel rows x 128 pixels (SASS UTMALDG)
               if (dbg & 4) {
-                ptx::mbar_arrive(&bars.raw_full[r]);
+                ptx::mbar_arrive_ws(&bars.raw_full[r]);
               } else {
-              ptx::mbar_arrive_expect_tx(&bars.raw_full[r], (uint32_t)kTcBK * kTcM * 4);
-              ptx::tma_load_2d(dst, &tmap_x0, p0, b * p.C0 + cx * kTcBK, &bars.raw_full[r]);
+              ptx::mbar_arrive_expect_tx_ws(&bars.raw_full[r], (uint32_t)kTcBK * kTcM * 4);
+              ptx::tma_load_2d_ws(dst, &tmap_x0, p0, b * p.C0 + cx * kTcBK, &bars.raw_full[r]);
               }
             } else {
-              ptx::mbar_arrive_expect_tx(&bars.raw_full[r], (uint32_t)nk * npx * 4);
+              ptx::mbar_arrive_expect_tx_ws(&bars.raw_full[r], (uint32_t)nk * npx * 4);
               for (int kk = 0; kk < nk; ++kk) {
                 const int k = cx * kTcBK + kk;
                 const float* src = (k < p.C0) ? p.x0 + ((size_t)b * p.C0 + k) * HW : p.x1 + ((size_t)b * p.C1 + (k - p.C0)) * HW;
-                ptx::bulk_g2s(dst + kk * kTcM, src + p0, (uint32_t)npx * 4, &bars.raw_full[r]);
+                ptx::bulk_g2s_ws(dst + kk * kTcM, src + p0, (uint32_t)npx * 4, &bars.raw_full[r]);
               }
             }
           }
@@ -647,8 +649,8 @@ k_inv_w_gemm_tc_v3(TcParams p, int B, int ntiles_per_img, const __grid_constant_
       }
     }
   } else if (warp == kK3WgtWarp) {
-    if (lane == 0) {
-      // ================================================================ B ring issue (packed weight chunks)
+    {
+      // ================================================================ B ring issue (warp-converged) (packed weight chunks)
       uint32_t g = 0, s = 0, sph = 1;
       for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
         int b, p0, h0, kspec, nsp;
@@ -656,12 +658,12 @@ k_inv_w_gemm_tc_v3(TcParams p, int B, int ntiles_per_img, const __grid_constant_
         for (int c = 0; c < nsp + nx; ++c, ++g) {
           if (g >= (uint32_t)NST) ptx::mbar_wait(&bars.empty[s], sph);
           if (c < nsp) {
-            ptx::mbar_arrive(&bars.full[s]);            // B of a spectral chunk is written by the convert warps
+            ptx::mbar_arrive_ws(&bars.full[s]);            // B of a spectral chunk is written by the convert warps
           } else if (dbg & 2) {
-            ptx::mbar_arrive(&bars.full[s]);
+            ptx::mbar_arrive_ws(&bars.full[s]);
           } else {
-            ptx::mbar_arrive_expect_tx(&bars.full[s], b_stage);
-            ptx::bulk_g2s(sB + s * b_stage, p.wpack + (size_t)(c - nsp) * (b_stage / 4), b_stage, &bars.full[s]);
+            ptx::mbar_arrive_expect_tx_ws(&bars.full[s], b_stage);
+            ptx::bulk_g2s_ws(sB + s * b_stage, p.wpack + (size_t)(c - nsp) * (b_stage / 4), b_stage, &bars.full[s]);
           }
           if (++s == (uint32_t)NST) { s = 0; sph ^= 1; }
         }
@@ -690,11 +692,14 @@ k_inv_w_gemm_tc_v3(TcParams p, int B, int ntiles_per_img, const __grid_constant_
       const bool has_res = p.res != nullptr && pvalid;
       const bool has_pre = p.pre != nullptr, do_gelu = p.act == PDES_ACT_GELU;
       const bool has_bias = p.bias != nullptr, bias_vec = aligned16(p.bias);
-      float cur[8], nxt[8];
+      // the residual (U-Net branch) is prefetched TWO column groups ahead: the epilogue is the pacing role of this kernel
+      // and, with one group in flight per warp (16 KB per SM), it ran at the latency of its own loads (~2900 cycles per group)
+      float cur[8], nxt[8], nx2[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const int n = qbeg * 8 + e;
         cur[e] = (has_res && qbeg < qend && n < N) ? __ldg(p.res + (obase + (uint32_t)n * uHW)) : 0.0f;
+        nxt[e] = (has_res && qbeg + 1 < qend && n + 8 < N) ? __ldg(p.res + (obase + (uint32_t)(n + 8) * uHW)) : 0.0f;
       }
       if (tid == 256) TRACE(3 * 512 + it * 4 + 0);
       ptx::mbar_wait(&bars.acc_full[a], (it / 2) & 1);
@@ -713,9 +718,9 @@ k_inv_w_gemm_tc_v3(TcParams p, int B, int ntiles_per_img, const __grid_constant_
       for (int qi = qbeg; qi < qend; ++qi) {
         const int n0 = qi * 8;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {                                // prefetch the residual of the next group
-          const int n = n0 + 8 + e;
-          nxt[e] = (has_res && qi + 1 < qend && n < N) ? __ldg(p.res + (obase + (uint32_t)n * uHW)) : 0.0f;
+        for (int e = 0; e < 8; ++e) {                                // prefetch the residual of the group after the next
+          const int n = n0 + 16 + e;
+          nx2[e] = (has_res && qi + 2 < qend && n < N) ? __ldg(p.res + (obase + (uint32_t)n * uHW)) : 0.0f;
         }
         uint32_t r[8];
         ptx::tmem_ld8(tbase + (uint32_t)n0, r);
@@ -767,7 +772,7 @@ k_inv_w_gemm_tc_v3(TcParams p, int B, int ntiles_per_img, const __grid_constant_
           }
         }
 #pragma unroll
-        for (int e = 0; e < 8; ++e) cur[e] = nxt[e];
+        for (int e = 0; e < 8; ++e) { cur[e] = nxt[e]; nxt[e] = nx2[e]; }
       }
       if (tid == 256) TRACE(3 * 512 + it * 4 + 3);
       if (qbeg >= qend) {                                            // no column group for this warp (N <= 8)

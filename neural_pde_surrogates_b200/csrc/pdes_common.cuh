@@ -63,17 +63,19 @@ int mix_dw_tma_launch(const float* X, const float* GO, float* gw1, float* gw2, i
 // tinv_f [2*m2][W]     K3b forward:  row 2l -> s_l cos(2 pi l w / W), row 2l+1 -> -s_l sin(..), s_l = c_l/(HW)
 // tinv_b [2*m2][W]     K3b backward: same with s_l = 1
 // herm   [m2]          s_l
+// twp    [m1+1][npp][2] K3a (v2): (cos, sin)(2 pi j p / H) for the folded row pairs p = 0 .. H/2 (npp = pairs rounded up to 8)
 struct TableLayout {
-  int nc4;
-  size_t twh, twa, tinv_f, tinv_b, herm, total;
+  int nc4, npp;
+  size_t twh, twa, tinv_f, tinv_b, herm, twp, total;
 };
 __host__ __device__ inline size_t round4(size_t n) { return (n + 3) & ~size_t(3); }
 __host__ __device__ inline TableLayout table_layout(int H, int W, int m1, int m2) {
-  (void)m1;
   TableLayout t;
   t.nc4 = (int)round4((size_t)2 * m2);
+  t.npp = (H / 2 + 1 + 7) / 8 * 8;
   t.twh = 0;
-  t.twa = t.twh + round4((size_t)2 * H);
+  t.twp = t.twh + round4((size_t)2 * H);                       // (offsets of twh and twp do not depend on W)
+  t.twa = t.twp + round4((size_t)(m1 + 1) * t.npp * 2);
   t.tinv_f = t.twa + (size_t)W * t.nc4;
   t.tinv_b = t.tinv_f + round4((size_t)2 * m2 * W);
   t.herm = t.tinv_b + round4((size_t)2 * m2 * W);

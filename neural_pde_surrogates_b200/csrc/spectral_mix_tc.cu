@@ -115,7 +115,7 @@ constexpr int kIh2HP = 8;                                // row pairs per thread
 constexpr int kIh2MaxWarps = 16;
 __global__ void __launch_bounds__(32 * kIh2MaxWarps)
 k_inv_h2(const float2* __restrict__ O2, SplitRule rule, int B, int C, int H, int m1, int m2,
-         const float* __restrict__ twh_g, float* __restrict__ Z) {
+         const float2* __restrict__ twp_g, float* __restrict__ Z) {
   PDES_DYN_SMEM(float2, sm2);
   const int K = 2 * m1, M2 = K * m2, J = 2 * m2, NJ = m1 + 1;
   const int npair = H / 2 + 1;
@@ -126,18 +126,25 @@ k_inv_h2(const float2* __restrict__ O2, SplitRule rule, int B, int C, int H, int
   const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, wq = tid >> 5, nwarp = nthr >> 5;
   const int o0 = blockIdx.x * 32, l = blockIdx.y, b = blockIdx.z;
   const int o = o0 + lane;
-  for (int idx = tid; idx < NJ * npp; idx += nthr) {
-    const int j = idx / npp, pp = idx - j * npp;
-    const int p = pp < npair ? pp : 0;
-    const int t = (int)(((unsigned)j * (unsigned)p) % (unsigned)H);
-    tw[idx] = make_float2(__ldg(twh_g + 2 * t), __ldg(twh_g + 2 * t + 1));
+  __shared__ unsigned char split_s[2 * 64 + 2];        // [k]: row k of this block's channel tiles carries a second partial
+  for (int idx = tid; idx < NJ * npp; idx += nthr) tw[idx] = __ldg(twp_g + idx);     // host-built table, coalesced
+  // the 32 channels of a block lie in at most two output-channel tiles of K2: flags for both
+  const int t_lo = o0 / rule.to, t_hi = (o0 + 31 < C ? o0 + 31 : C - 1) / rule.to;
+  for (int k = tid; k < K; k += nthr) {
+    const int m = k * m2 + l;
+    unsigned char f = 0;
+    if (item_is_split(rule, m * rule.ntile + t_lo)) f |= 1;
+    if (item_is_split(rule, m * rule.ntile + t_hi)) f |= 2;
+    if (k < 2 * 64) split_s[k] = f;
   }
+  __syncthreads();
+  const int o_hi0 = (t_lo + 1) * rule.to;              // first channel of the upper tile
   const size_t pstride = (size_t)M2 * B * C;
   auto load_o = [&](int k, int oo) -> float2 {         // O[k][l] of channel oo (both partials where the item was split)
-    const int m = k * m2 + l;
-    const size_t at = ((size_t)m * B + b) * C + oo;
+    const size_t at = ((size_t)(k * m2 + l) * B + b) * C + oo;
     float2 v = __ldg(O2 + at);
-    if (item_is_split(rule, m * rule.ntile + oo / rule.to)) {
+    const unsigned char f = (k < 2 * 64) ? split_s[k] : (unsigned char)(item_is_split(rule, (k * m2 + l) * rule.ntile + oo / rule.to) ? 3 : 0);
+    if (f & (oo >= o_hi0 ? 2 : 1)) {
       const float2 u = __ldg(O2 + pstride + at);
       v.x += u.x; v.y += u.y;
     }
@@ -350,58 +357,54 @@ k_mix_tc(MtParams p, const __grid_constant__ CUtensorMap tmap_w, const __grid_co
       const uint32_t idesc = ptx::idesc_tf32(128, npad);
       const uint32_t sbase = ptx::smem_u32(base);
       const uint64_t kstepb = (uint64_t)((2u * lbo) >> 4);                   // B: 8 k = two k-quads
-      int kc = kc_first + q, part = 0;
-      while (kc >= p.nck) { kc -= p.nck; ++part; }
+      // Every issuer walks EVERY part of the CTA's range with the same protocol -- wait for the accumulator buffer to be
+      // drained, issue its chunks of the part (possibly none), commit acc_full -- so an arrival for part P can never land
+      // on acc_full[a] before the phase of part P - nbuf has completed (an issuer without chunks in a short part would
+      // otherwise run ahead and complete that phase early: seen as a rare wrong result with nck < 4).
       int s = q;
       uint32_t fph = 0;
-      int done_part = 0;                                                     // parts whose acc_full this issuer has committed
-      bool fresh = true;
-      for (int g = q; g < nloc; g += kMtNIssue) {
-        while (done_part < part) {                                           // close the parts that ended before this chunk
-          ptx::tc_commit_ws(&bars.acc_full[(nbuf == 2) ? (done_part & 1) : 0]);
-          ++done_part;
-          fresh = true;
-        }
+      int g = q;                                                             // next local chunk of this issuer
+      int pb = 0, pe = p.nck - kc_first;                                     // local chunk range [pb, pe) of the current part
+      for (int part = 0; pb < nloc; ++part) {
+        if (pe > nloc) pe = nloc;
         const uint32_t a = (nbuf == 2) ? (uint32_t)(part & 1) : 0u;
-        if (fresh && part >= nbuf) {
+        if (part >= nbuf) {
           ptx::mbar_wait(&bars.acc_empty[a], (uint32_t)((((nbuf == 2) ? (part >> 1) : part) - 1) & 1));
           ptx::tc_fence_after();
         }
-        if (q == 0 && lane == 0) MT_TRACE(2, g, 0);
-        ptx::mbar_wait(&bars.full[s], fph);
-        if (q == 0 && lane == 0) MT_TRACE(2, g, 1);
-        ptx::tc_fence_after();
         const uint32_t dacc = tmem_base + (a * 4u + (uint32_t)q) * (uint32_t)npad;
-        const uint32_t sst = sbase + (uint32_t)s * stage_bytes;
-        const uint64_t a_hi = mt_desc_sw128(sst);                            // + 2 (= 32 bytes) per k-step of 8
-        const uint64_t b_hi = ptx::smem_desc_noswizzle(sst + b_off, lbo, 128), b_lo = b_hi + (uint64_t)(blk >> 4);
-        const uint32_t a_lo = tmem_base + ta0 + (uint32_t)s * 32u;
-        if (!MT_DBG(1)) {
-          ptx::mma_tf32_ws(dacc, a_hi, b_hi, idesc, fresh ? 0u : 1u);                           // hi * hi
-          ptx::mma_tf32_ws(dacc, a_hi + 2, b_hi + kstepb, idesc, 1u);
-          ptx::mma_tf32_ws(dacc, a_hi + 4, b_hi + 2 * kstepb, idesc, 1u);
-          ptx::mma_tf32_ws(dacc, a_hi + 6, b_hi + 3 * kstepb, idesc, 1u);
-          ptx::mma_tf32_ws(dacc, a_hi, b_lo, idesc, 1u);                                        // hi * lo
-          ptx::mma_tf32_ws(dacc, a_hi + 2, b_lo + kstepb, idesc, 1u);
-          ptx::mma_tf32_ws(dacc, a_hi + 4, b_lo + 2 * kstepb, idesc, 1u);
-          ptx::mma_tf32_ws(dacc, a_hi + 6, b_lo + 3 * kstepb, idesc, 1u);
-          ptx::mma_tf32_ta_ws(dacc, a_lo, b_hi, idesc, 1u);                                     // lo * hi
-          ptx::mma_tf32_ta_ws(dacc, a_lo + 8, b_hi + kstepb, idesc, 1u);
-          ptx::mma_tf32_ta_ws(dacc, a_lo + 16, b_hi + 2 * kstepb, idesc, 1u);
-          ptx::mma_tf32_ta_ws(dacc, a_lo + 24, b_hi + 3 * kstepb, idesc, 1u);
+        bool fresh = true;
+        for (; g < pe; g += kMtNIssue) {
+          if (q == 0 && lane == 0) MT_TRACE(2, g, 0);
+          ptx::mbar_wait(&bars.full[s], fph);
+          if (q == 0 && lane == 0) MT_TRACE(2, g, 1);
+          ptx::tc_fence_after();
+          const uint32_t sst = sbase + (uint32_t)s * stage_bytes;
+          const uint64_t a_hi = mt_desc_sw128(sst);                          // + 2 (= 32 bytes) per k-step of 8
+          const uint64_t b_hi = ptx::smem_desc_noswizzle(sst + b_off, lbo, 128), b_lo = b_hi + (uint64_t)(blk >> 4);
+          const uint32_t a_lo = tmem_base + ta0 + (uint32_t)s * 32u;
+          if (!MT_DBG(1)) {
+            ptx::mma_tf32_ws(dacc, a_hi, b_hi, idesc, fresh ? 0u : 1u);                         // hi * hi
+            ptx::mma_tf32_ws(dacc, a_hi + 2, b_hi + kstepb, idesc, 1u);
+            ptx::mma_tf32_ws(dacc, a_hi + 4, b_hi + 2 * kstepb, idesc, 1u);
+            ptx::mma_tf32_ws(dacc, a_hi + 6, b_hi + 3 * kstepb, idesc, 1u);
+            ptx::mma_tf32_ws(dacc, a_hi, b_lo, idesc, 1u);                                      // hi * lo
+            ptx::mma_tf32_ws(dacc, a_hi + 2, b_lo + kstepb, idesc, 1u);
+            ptx::mma_tf32_ws(dacc, a_hi + 4, b_lo + 2 * kstepb, idesc, 1u);
+            ptx::mma_tf32_ws(dacc, a_hi + 6, b_lo + 3 * kstepb, idesc, 1u);
+            ptx::mma_tf32_ta_ws(dacc, a_lo, b_hi, idesc, 1u);                                   // lo * hi
+            ptx::mma_tf32_ta_ws(dacc, a_lo + 8, b_hi + kstepb, idesc, 1u);
+            ptx::mma_tf32_ta_ws(dacc, a_lo + 16, b_hi + 2 * kstepb, idesc, 1u);
+            ptx::mma_tf32_ta_ws(dacc, a_lo + 24, b_hi + 3 * kstepb, idesc, 1u);
+          }
+          ptx::tc_commit_ws(&bars.empty[s]);
+          if (q == 0 && lane == 0) MT_TRACE(2, g, 2);
+          fresh = false;
+          s += 4; if (s >= NST) { s -= NST; fph ^= 1u; }
         }
-        ptx::tc_commit_ws(&bars.empty[s]);
-        if (q == 0 && lane == 0) MT_TRACE(2, g, 2);
-        fresh = false;
-        s += 4; if (s >= NST) { s -= NST; fph ^= 1u; }
-        kc += kMtNIssue;
-        while (kc >= p.nck) { kc -= p.nck; ++part; }
-      }
-      int nparts = 1;                                                        // close the remaining parts of this CTA's range
-      { int e = p.nck - kc_first; while (e < nloc) { e += p.nck; ++nparts; } }
-      while (done_part < nparts) {
-        ptx::tc_commit_ws(&bars.acc_full[(nbuf == 2) ? (done_part & 1) : 0]);
-        ++done_part;
+        ptx::tc_commit_ws(&bars.acc_full[a]);
+        pb = pe;
+        pe += p.nck;
       }
     }
   } else if (warp >= kMtTma0 && warp < kMtTma0 + 4) {
@@ -671,7 +674,8 @@ int pdes_inv_h_modes(const float* O2, int B, int Cin, int C, int H, int m1, int 
   if (smem > 48 * 1024) PDES_SET_SMEM(kfn, smem);
   PDES_MAX_CARVEOUT(kfn);
   PDES_LAUNCH(kfn, dim3((unsigned)ceil_div(C, 32), (unsigned)m2, (unsigned)B), dim3((unsigned)(32 * nwarp)), smem, stream,
-              reinterpret_cast<const float2*>(O2), rule, B, C, H, m1, m2, tables /* twh [H][2] sits at offset 0 of the blob */, Z);
+              reinterpret_cast<const float2*>(O2), rule, B, C, H, m1, m2,
+              reinterpret_cast<const float2*>(tables + table_layout(H, 2, m1, m2).twp), Z);
   return check_launch("pdes_inv_h_modes");
 }
 
