@@ -373,13 +373,14 @@ def leg_rollout(hx: Harness, args, wl: Workload, tr, model, pde):
     kw = dict(compute_loss=False, include_data=True, nr_gt_steps=1, t_res=wl.tw * (nsteps + 1), spatial_conditioning=mask,
               use_bc=False, divide_by_t=False)
     res, ok, finite, err = {}, 1.0, True, ""
-    modes = ("eager", "graph") if hx.graphs else ("eager",)
+    modes = ("eager", "graph", "graph_k") if hx.graphs else ("eager",)
     model.eval()
     try:
         with torch.no_grad():
             for mode in modes:
-                tr.simulate(u, cond, pos, graph=(mode == "graph"), **dict(kw, t_res=wl.tw * 3))   # warm-up / capture
-                res[mode] = hx.timed(lambda: tr.simulate(u, cond, pos, graph=(mode == "graph"), **kw), 1)
+                gk = dict(graph=(mode != "eager"), steps_per_graph=(args.rollout_steps_per_graph if mode == "graph_k" else 1))
+                tr.simulate(u, cond, pos, **gk, **dict(kw, t_res=wl.tw * (1 + max(2, gk["steps_per_graph"]))))   # warm-up / capture
+                res[mode] = hx.timed(lambda: tr.simulate(u, cond, pos, **gk, **kw), 1)
             preds = tr.simulate(u, cond, pos, graph=hx.graphs, **dict(kw, t_res=wl.tw * 3))
             finite = bool(torch.isfinite(preds[-1]).all())
     except Exception as exc:                                              # noqa: BLE001  (no collective was pending)
@@ -397,6 +398,9 @@ def leg_rollout(hx: Harness, args, wl: Workload, tr, model, pde):
         out["eager"] = n_total * nsteps / (res["eager"] * 1e-3)
         if "graph" in res:
             out["cuda_graph"] = n_total * nsteps / (res["graph"] * 1e-3)
+        if "graph_k" in res:
+            out["cuda_graph_multi_step"] = n_total * nsteps / (res["graph_k"] * 1e-3)
+            out["steps_per_graph"] = args.rollout_steps_per_graph
     else:
         out["error"] = err or "failed on another rank"
     return out
@@ -419,6 +423,41 @@ def leg_unroll8(hx: Harness, args, wl: Workload, tr, pde):
     ms8 = hx.timed(step_u8, n8) / n8
     return {"metric": "train_samples_per_s", "unroll": args.unroll, "value": B * hx.world / (ms8 * 1e-3), "ms_per_step": ms8,
             "n_gpus": hx.world, "note": f"whole job; {args.unroll} no-grad model applications + 1 with grad per optimizer step"}
+
+
+def leg_train_graph(hx: Harness, args, wl: Workload):
+    """The same optimizer step replayed from ONE CUDA graph (GraphedTrainStep), at the headline batch and at the
+    reference's CPU-runnable batch 4 (an eager step there is ~1800 launches and host-launch-bound)."""
+    from neural_pde_surrogates_b200.trainer import AutoregressivePushforwardTrainer
+    out = {}
+    dev = hx.dev
+    for B in sorted({4, args.batch}):
+        try:
+            model, pde = build(dev, wl)
+            opt = torch.optim.Adam(model.parameters(), lr=1e-4, capturable=True)
+            tr = AutoregressivePushforwardTrainer(model, pde, optimizer=opt, device=dev, batch_size=B,
+                                                  base_resolution=(501, wl.H, wl.W))
+            u, labels, mask, pos = synthetic_batch(B, pde, torch.Generator().manual_seed(21), wl)
+            u_h, labels_h = hx.pin(u), hx.pin(labels)
+            u, labels, mask, pos = u.to(dev), labels.to(dev), mask.to(dev), pos.to(dev)
+            cond = torch.empty(B, 0, device=dev)
+            gs = tr.graphed_train_step(u, labels, pos, cond, mask)
+
+            def step_e2e():
+                return float(gs(u_h, labels_h))                                   # H2D of the windows + D2H of the loss
+            for _ in range(2):
+                step_e2e()
+            n = max(3, min(args.steps, 10))
+            ms = hx.timed(lambda: gs(u, labels), n) / n
+            ms_e2e = hx.timed(step_e2e, n) / n
+            out[f"batch{B}"] = {"train_samples_per_s": B / (ms * 1e-3), "ms_per_step": ms, "e2e_samples_per_s": B / (ms_e2e * 1e-3),
+                                "kernel_launches_of_ours_per_replay": gs.launches_per_replay}
+            del gs, tr, opt, model
+        except Exception as exc:                                          # noqa: BLE001
+            out[f"batch{B}"] = {"error": repr(exc)[:200]}
+        torch.cuda.empty_cache()
+    out["note"] = "whole optimizer step (forward, backward, Adam) captured in one CUDA graph and replayed; same work as the eager headline"
+    return out
 
 
 def leg_other_configs(hx: Harness, args):
@@ -493,6 +532,8 @@ def run_legs(hx: Harness, args, wl: Workload = WL):
     if not args.no_extras:
         extra["rollout"] = leg_rollout(hx, args, wl, t["trainer"], t["model"], t["pde"])
         extra["train_unroll8"] = leg_unroll8(hx, args, wl, t["trainer"], t["pde"])
+        if hx.world == 1 and hx.graphs:
+            extra["train_cuda_graph"] = leg_train_graph(hx, args, wl)
         if hx.world == 1 and not args.no_other_configs:
             extra.update(leg_other_configs(hx, args))
     line = None
@@ -547,6 +588,7 @@ def make_parser():
     ap.add_argument("--batch", type=int, default=16, help="per-GPU batch (config default, defaults/base.py:6)")
     ap.add_argument("--rollout-batch", type=int, default=16, help="trajectories per GPU in the rollout leg")
     ap.add_argument("--rollout-steps", type=int, default=50)
+    ap.add_argument("--rollout-steps-per-graph", type=int, default=10, help="model applications per CUDA-graph replay")
     ap.add_argument("--unroll", type=int, default=8)
     ap.add_argument("--tf32-convs", action="store_true", help="let cuDNN use TF32 in the U-Net branch (reported separately)")
     ap.add_argument("--no-cudnn-benchmark", action="store_true",

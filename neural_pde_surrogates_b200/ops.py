@@ -73,6 +73,11 @@ def counters():
     return dict(_counters)
 
 
+def add_launches(n: int):
+    """Account for kernels launched by a CUDA-graph replay (the Python-side counter does not run during a replay)."""
+    _counters["launches"] += int(n)
+
+
 def enable_timing(flag: bool):
     _timing["on"] = bool(flag)
     if flag:

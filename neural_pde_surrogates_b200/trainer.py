@@ -98,6 +98,100 @@ class GraphedModelStep:
         return self.out
 
 
+class GraphedRollout:
+    """K consecutive model applications captured in ONE CUDA graph: the state [B,1,tw,H,W] is handed from one
+    application to the next inside the graph (no host round trip, no per-step copy); the K predictions stay in static
+    buffers and are copied out once per replay.  Replaying ceil(n / K) times gives an n-step rollout."""
+
+    def __init__(self, model, u, cond, pos, spatial_cond, steps_per_graph: int, warmup: int = 2):
+        own = lambda t: None if t is None else t.detach().clone()
+        self.K = int(steps_per_graph)
+        self.u = own(u)
+        self.static = dict(cond=own(cond), pos=own(pos), spatial_cond=own(spatial_cond))
+        self.kw = dict(cond=self.static["cond"], bc=None, pos=self.static["pos"], t_cond=None,
+                       spatial_cond=self.static["spatial_cond"])
+        side = torch.cuda.Stream(device=u.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(warmup):
+                model(self.u, **self.kw)
+        torch.cuda.current_stream().wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph), torch.no_grad():
+            outs, state = [], self.u
+            for _ in range(self.K):
+                state = model(state, **self.kw)
+                outs.append(state)
+            self.outs = outs
+
+    def matches(self, u, cond, pos, spatial_cond) -> bool:
+        sig = lambda t: None if t is None else (tuple(t.shape), t.dtype, t.device)
+        return (sig(u), sig(cond), sig(pos), sig(spatial_cond)) == \
+            (sig(self.u), *(sig(self.static[k]) for k in ("cond", "pos", "spatial_cond")))
+
+    def __call__(self, u, cond=None, pos=None, spatial_cond=None):
+        """Returns the K predictions that follow `u` (views of static buffers: clone before the next replay)."""
+        for k, t in (("cond", cond), ("pos", pos), ("spatial_cond", spatial_cond)):
+            buf = self.static[k]
+            if buf is not None and t is not None and buf.numel() and t.data_ptr() != buf.data_ptr():
+                buf.copy_(t)
+        if u.data_ptr() != self.u.data_ptr():
+            self.u.copy_(u)
+        self.graph.replay()
+        return self.outs
+
+
+class GraphedTrainStep:
+    """One whole optimizer step -- push-forward applications, differentiated application, loss, backward, gradient
+    all-reduce, Adam -- captured in ONE CUDA graph and replayed with new windows copied into static buffers.
+    At the reference's CPU-runnable batch (4) an eager step is ~1800 kernel launches and host-launch-bound; a replay is
+    one launch.  Needs a capturable optimizer (`torch.optim.Adam(..., capturable=True)`) and fixed shapes / unroll count
+    (one graph per unroll count).  The packed tensor-core operands of the weights are rebuilt inside the graph on every
+    replay, so the weights the replay uses are always the current ones."""
+
+    def __init__(self, trainer, data, labels, x, conditioning, spatial_conditioning, unrolled: int = 0, warmup: int = 3):
+        own = lambda t: None if t is None else t.detach().clone()
+        self.tr, self.unrolled = trainer, int(unrolled)
+        self.data, self.labels = own(data), own(labels)
+        self.next_labels = [own(labels) for _ in range(self.unrolled)]        # labels of the windows after each unroll
+        self.x, self.cond, self.sc = own(x), own(conditioning), own(spatial_conditioning)
+        for group in trainer.optimizer.param_groups:
+            if not group.get("capturable", False):
+                raise ValueError("GraphedTrainStep needs a capturable optimizer, e.g. torch.optim.Adam(params, capturable=True)")
+        side = torch.cuda.Stream(device=data.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):                                           # cuDNN autotuning, lazy state, table caches
+                self._step()
+        torch.cuda.current_stream().wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        from . import ops
+        before = ops.counters()["launches"]
+        with torch.cuda.graph(self.graph):
+            self.loss = self._step()
+        self.launches_per_replay = ops.counters()["launches"] - before       # our own kernels inside one replay
+
+    def _step(self):
+        nl = (lambda k: self.next_labels[k - 1]) if self.unrolled else None
+        loss, _ = self.tr.train_step_windows(self.data, self.labels if not self.unrolled else self.next_labels[-1], self.x,
+                                             self.cond, self.sc, unrolled=self.unrolled, next_labels=nl)
+        self.tr.optimizer_step(loss)
+        return loss.detach()
+
+    def __call__(self, data, labels, next_labels=None):
+        """Copy the new windows in, replay, return the (static) loss tensor."""
+        self.data.copy_(data, non_blocking=True)
+        if self.unrolled:
+            for k in range(self.unrolled):
+                self.next_labels[k].copy_(next_labels(k + 1), non_blocking=True)
+        else:
+            self.labels.copy_(labels, non_blocking=True)
+        self.graph.replay()
+        from . import ops
+        ops.add_launches(self.launches_per_replay)
+        return self.loss
+
+
 class AutoregressivePushforwardTrainer:
     model_interface = [M.AR_TB]
 
@@ -171,6 +265,15 @@ class AutoregressivePushforwardTrainer:
         self.optimizer.step()
 
     # ------------------------------------------------------------------------------------------ rollout
+    def graphed_train_step(self, data, labels, x, conditioning, spatial_conditioning, unrolled: int = 0):
+        """The CUDA-graph version of train_step_windows + optimizer_step for these shapes (built on first use)."""
+        key = ("train", tuple(data.shape), int(unrolled), data.device.index)
+        g = self._graphs.get(key)
+        if g is None:
+            g = GraphedTrainStep(self, data, labels, x, conditioning, spatial_conditioning, unrolled)
+            self._graphs[key] = g
+        return g
+
     def _model_step(self, pred, conditioning, x, spatial_cond, graph: bool):
         if not graph:
             return self.model(pred, cond=conditioning, bc=None, pos=x, t_cond=None, spatial_cond=spatial_cond)
@@ -183,7 +286,7 @@ class AutoregressivePushforwardTrainer:
 
     def simulate(self, u, conditioning, x, compute_loss, include_data, nr_gt_steps, t_res,
                  t_conditioning=torch.empty(0), spatial_conditioning=torch.empty(0), clip_min=True, use_bc=True,
-                 u_bc=None, u_mask=None, divide_by_t=True, graph: bool = False):
+                 u_bc=None, u_mask=None, divide_by_t=True, graph: bool = False, steps_per_graph: int = 1):
         """Autoregressive rollout with the reference's signature and return conventions (:288-440).
         Returns: losses | data_pred | (losses, (data_gt, data_pred)) depending on compute_loss / include_data."""
         tw = self.data_creator.tw
@@ -208,9 +311,23 @@ class AutoregressivePushforwardTrainer:
         data_gt, data_pred, losses = [pred], [pred], []
         n_t = 0
         npix = math.prod(self.config.base_resolution[1:])
-        for step in range(tw * nr_gt_steps, t_res - tw + 1, tw):
+        steps = list(range(tw * nr_gt_steps, t_res - tw + 1, tw))
+        chain, queue = None, []
+        if graph and steps_per_graph > 1 and len(steps) >= steps_per_graph:
+            # K model applications per graph replay: the state is handed on inside the graph (GraphedRollout)
+            key = ("rollout", tuple(pred.shape), int(steps_per_graph), pred.device.index)
+            chain = self._graphs.get(key)
+            if chain is None or not chain.matches(pred, conditioning, x, spatial_cond):
+                chain = GraphedRollout(self.model, pred, conditioning, x, spatial_cond, steps_per_graph)
+                self._graphs[key] = chain
+        for i, step in enumerate(steps):
             labels = u[:, :, step:step + tw].to(dev) if compute_loss else None
-            pred = self._model_step(pred, conditioning, x, spatial_cond, graph)
+            if chain is not None and (queue or len(steps) - i >= chain.K):
+                if not queue:
+                    queue = [o.clone() for o in chain(pred, conditioning, x, spatial_cond)]
+                pred = queue.pop(0)
+            else:
+                pred = self._model_step(pred, conditioning, x, spatial_cond, graph)
             if compute_loss and use_mask:
                 lm = u_mask[:, :, step:step + tw].to(dev)
                 pred, labels = pred * lm, labels * lm

@@ -166,6 +166,57 @@ def test_graph_replay_sees_new_conditioning_and_weights():
         assert rel_l2(a, b) < 1e-6
 
 
+def test_graphed_train_step_equals_eager_steps():
+    """Whole optimizer step in one CUDA graph (GraphedTrainStep) == the same number of eager steps: same loss, same weights."""
+    model, pde, g = tiny_model(DEV)
+    twin = copy.deepcopy(model)
+    B = g["u"].shape[0]
+    u, mask, labels = (torch.from_numpy(g[k]).to(DEV) for k in ("u", "mask", "labels"))
+    pos = pde.x.to(DEV)[None].repeat(B, 1, 1, 1)
+    cond = torch.empty(B, 0, device=DEV)
+    for unrolled in (0, 2):
+        m_e, m_g = copy.deepcopy(model), copy.deepcopy(twin)
+        tr_e = AutoregressivePushforwardTrainer(m_e, pde, optimizer=torch.optim.Adam(m_e.parameters(), lr=1e-4), device=DEV,
+                                                batch_size=B, base_resolution=(501, 24, 16))
+        tr_g = AutoregressivePushforwardTrainer(m_g, pde, optimizer=torch.optim.Adam(m_g.parameters(), lr=1e-4, capturable=True),
+                                                device=DEV, batch_size=B, base_resolution=(501, 24, 16))
+        nl = (lambda k: labels) if unrolled else None
+        gs = tr_g.graphed_train_step(u, labels, pos, cond, mask, unrolled=unrolled)        # 3 warm-up steps + capture
+        lg = gs(u, labels, next_labels=nl).clone()                                          # 4th step = first replay
+        lg2 = gs(u, labels, next_labels=nl).clone()                                         # 5th step
+        for _ in range(5):
+            le, _ = tr_e.train_step_windows(u, labels, pos, cond, mask, unrolled=unrolled, next_labels=nl)
+            tr_e.optimizer_step(le)
+            if _ == 3:
+                l4 = le.detach().clone()
+        assert abs(lg.item() - l4.item()) <= 2e-5 * abs(l4.item()), (unrolled, lg.item(), l4.item())
+        assert abs(lg2.item() - le.item()) <= 2e-5 * abs(le.item()), (unrolled, lg2.item(), le.item())
+        for (k, a), b in zip(m_g.named_parameters(), m_e.parameters()):
+            assert rel_l2(a, b) < 1e-5, (unrolled, k, rel_l2(a, b))
+        assert gs.launches_per_replay > 0
+
+
+def test_k_step_rollout_graph_equals_eager():
+    """GraphedRollout: K model applications per graph replay, state handed on inside the graph (plus the tail steps)."""
+    model, pde, g = tiny_model(DEV)
+    model.eval()
+    B = g["u"].shape[0]
+    u = torch.from_numpy(g["u"]).to(DEV)
+    mask = torch.from_numpy(g["mask"]).to(DEV)
+    pos = pde.x.to(DEV)[None].repeat(B, 1, 1, 1)
+    cond = torch.empty(B, 0, device=DEV)
+    tr = AutoregressivePushforwardTrainer(model, pde, device=DEV, batch_size=B, base_resolution=(501, 24, 16))
+    kw = dict(compute_loss=False, include_data=True, nr_gt_steps=1, t_res=25 * 9, use_bc=False, divide_by_t=False,
+              spatial_conditioning=mask)
+    with torch.no_grad():
+        ref = tr.simulate(u, cond, pos, graph=False, **kw)
+        out = tr.simulate(u, cond, pos, graph=True, steps_per_graph=3, **kw)                # 8 steps = 2 replays + 2 single steps
+        out2 = tr.simulate(u, cond, pos, graph=True, steps_per_graph=3, **kw)               # replays the cached graphs
+    assert len(out) == len(ref) == 9
+    for a, b, c in zip(out[1:], ref[1:], out2[1:]):
+        assert rel_l2(a, b) < 1e-6 and rel_l2(c, b) < 1e-6
+
+
 def test_packed_weight_cache_follows_data_writes():
     """`.data` writes do not bump Parameter._version; ops.invalidate_weight_caches() must refresh the packed
     1x1 operands, and in-place optimizer-style updates must be picked up without it."""
