@@ -153,6 +153,16 @@ int pdes_timeconv_backward(const float* z, const float* gy, const float* w1, con
                            const float* b2, float* dz, float* dw1, float* db1, float* dw2, float* db2, float* ws, int B,
                            int HW, int time_window, int act, void* stream);
 
+/* ---- per-step wrapper: fused output constraints of one model application (no autograd) -----------
+ * out[b,0,t,:] = mask(volume_rescale(mask(tanh(x[b,0,tw-1,:] + steps[t] * delta[b,0,t,:]))))   replaces add_delta
+ * (dec_grid.py:8-23), the final activation, the obstacle masking and the 'individual_static' approximate volume
+ * preservation of activation_wrapper.py:33-106 (~25 element-wise / reduction launches) for one field (num_c = 1).
+ * delta, x, out: [B][tw][HW]; mask: [B][...] with batch stride mask_bstride, channel 0 used (NULL if !use_mask);
+ * steps, cap: [tw] (the reference's cumulative sums of dt and of max_pct_dif). */
+int pdes_constrain_forward(const float* delta, const float* x, const float* mask, int mask_bstride, const float* steps,
+                           const float* cap, float* out, int B, int tw, int HW, int use_tanh, int use_mask,
+                           int use_volume, void* stream);
+
 /* ---- U-Net branch: 1x1 convolutions on the K3b / wgrad tensor-core kernels ---------------
  * Replaces forward and backward of the nn.Conv2d(k=1) layers of the reference's ResidualBlock shortcut
  * (proc_unet_modern.py:219-222) -- cuDNN runs them as SIMT sgemm at ~27 TFLOP/s.

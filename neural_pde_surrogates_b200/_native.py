@@ -55,6 +55,7 @@ _PROTOTYPES = {
     "pdes_timeconv_forward": (c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "pdes_timeconv_bwd_workspace_floats": (c_size_t, [_I, _I, _I]),
     "pdes_timeconv_backward": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "pdes_constrain_forward": (c_int, [_P, _P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "pdes_conv1x1_tc_ok": (c_int, [_I, _I, _I, _I, _P]),
     "pdes_conv1x1_tc": (c_int, [_P, _I, _P, _P, _P, _P, c_size_t, _I, _I, _I, _I, _P]),
     "pdes_wgrad_tc_range": (c_int, [_P, _P, _I, _I, _I, _P, _I, _P, _P, _I, _I, _I, _P]),

@@ -607,3 +607,29 @@ def timeconv_decoder(z, decoder, num_c: int, time_window: int):
             return TimeConvFunction.apply(zc, c1.weight, c1.bias, c2.weight, c2.bias, code)
     zz = z.permute(0, 2, 3, 1).reshape(B * H * W, num_c, time_window * 3)
     return decoder(zz).view(B, H, W, num_c, time_window).permute(0, 3, 4, 1, 2)
+
+
+# ---- per-step wrapper: fused output constraints (csrc/constrain.cu), inference / no-grad applications only -----------
+enable_fused_constraints = True
+
+
+def constrain_forward(delta, x, mask, steps, cap, use_tanh: bool, use_mask: bool, use_volume: bool):
+    """mask(volume_rescale(mask(tanh(x[:, :, -1:] + steps * delta)))) for one field; delta, x: [B, 1, tw, H, W]."""
+    lib = _lib()
+    _check_f32_cuda("delta", delta, 5)
+    _check_f32_cuda("x", x, 5)
+    B, C, tw, H, W = delta.shape
+    if C != 1 or tuple(x.shape) != tuple(delta.shape):
+        raise ValueError("constrain_forward handles one field with matching state / delta shapes")
+    delta, x = delta.contiguous(), x.contiguous()
+    p = lambda t: None if t is None else t.data_ptr()
+    with torch.cuda.device(delta.device):
+        out = torch.empty_like(delta)
+        mk = None
+        if use_mask:
+            mk = mask if mask.is_contiguous() else mask.contiguous()
+        _native.check(lib, lib.pdes_constrain_forward(p(delta), p(x), p(mk), (mk.shape[1] * H * W) if mk is not None else 0,
+                                                      p(steps), p(cap), p(out), B, tw, H * W, int(use_tanh), int(use_mask),
+                                                      int(use_volume), _stream()))
+        _counters["launches"] += 1
+    return out

@@ -74,12 +74,17 @@ class TimeConvDense(nn.Module):
         self.decoder = nn.Sequential(nn.Conv1d(num_c, num_c * 2, ka, stride=2), activation,
                                      nn.Conv1d(num_c * 2, num_c, kb, stride=1))
 
-    def forward(self, h, u, **kwargs):
+    def delta(self, h):
         z = ops.conv1x1(h, self.pre_decoder)                     # [b, 3*tw*c, H, W]
-        delta = ops.timeconv_decoder(z, self.decoder, self.num_c, self.time_window)   # [b, c, tw, H, W]
+        return ops.timeconv_decoder(z, self.decoder, self.num_c, self.time_window)   # [b, c, tw, H, W]
+
+    def steps(self, device):
+        """cumsum(dt) over the time window, exactly as add_delta builds it (dec_grid.py:8-23)."""
         dt = self.pde.dt if self.dec_delta_dt else 1
-        steps = torch.cumsum(torch.full((1, 1, self.time_window, 1, 1), dt, device=h.device), dim=2)
-        return u[:, :, -1:] + steps * delta
+        return torch.cumsum(torch.full((1, 1, self.time_window, 1, 1), dt, device=device), dim=2)
+
+    def forward(self, h, u, **kwargs):
+        return u[:, :, -1:] + self.steps(h.device) * self.delta(h)
 
 
 _REGISTRY = {"FNO": FNO, "UFNO": UFNO, "UNetModern": UNetModern,
@@ -181,7 +186,36 @@ class ConstrainedSurrogate(EncProcDec):
         m = spatial_cond[:, self.spatial_cond_channel][:, None, None]
         return u - m * u
 
+    def _fused_ok(self, x, spatial_cond):
+        return (ops.enable_fused_constraints and not torch.is_grad_enabled() and x.is_cuda and x.dtype == torch.float32
+                and self.num_c == 1 and x.dim() == 5 and isinstance(self.decoder, TimeConvDense)
+                and isinstance(self.activation_final, (nn.Tanh, nn.Identity))
+                and (not self.enforce_spatial_cond or (spatial_cond is not None and spatial_cond.numel() > 0
+                                                       and self.spatial_cond_channel == 0)))
+
+    def _consts(self, device, tw):
+        key = (str(device), tw)
+        if getattr(self, "_const_key", None) != key:
+            steps = self.decoder.steps(device).reshape(-1).contiguous()
+            cap = torch.cumsum(torch.full((tw,), float(self.max_pct_dif), device=device, dtype=torch.float32), dim=0)   # :86-88
+            self._const_key, self._const_val = key, (steps, cap)
+        return self._const_val
+
     def forward(self, x, cond=None, bc=None, pos=None, t_cond=None, spatial_cond=None):
+        if self._fused_ok(x, spatial_cond):
+            # no-grad application (rollout, push-forward unroll): add_delta + tanh + masking + volume rescale in ONE kernel
+            if self._none_if_empty(bc) is not None or self._none_if_empty(t_cond) is not None:
+                raise NotImplementedError("time-varying conditioning needs a bc_encoder, which the twophase configs do not use")
+            vb = self.conditioning(x, cond, spatial_cond)
+            h = self.encoder(u=x, variables_broadcast=vb, pos=pos)
+            for i, p in enumerate(self.processor):
+                nxt = p(h=h, variables_broadcast=vb, pos=pos)
+                h = nxt + h if (self.processor_residual and i > 0) else nxt
+            delta = self.decoder.delta(h)
+            steps, cap = self._consts(x.device, x.shape[2])
+            return ops.constrain_forward(delta, x, spatial_cond if self.enforce_spatial_cond else None, steps, cap,
+                                         isinstance(self.activation_final, nn.Tanh), self.enforce_spatial_cond,
+                                         self.approx_volume_preserve)
         u = self.activation_final(super().forward(x, cond=cond, bc=bc, pos=pos, t_cond=t_cond, spatial_cond=spatial_cond))
         if self.enforce_spatial_cond:
             u = self._mask_out(spatial_cond, u)

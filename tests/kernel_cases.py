@@ -488,3 +488,37 @@ def check_timeconv(be, B=2, HW=200, act=1, tw=25):
     for k, v in errs.items():
         assert v < TOL, f"timeconv {k}: {v:.3e}"
     return errs
+
+
+def check_constrain(be, B=3, tw=5, H=9, W=7, n_spatial=2, use_tanh=1, use_mask=1, use_volume=1):
+    """Fused output constraints (csrc/constrain.cu) vs the reference formulas of activation_wrapper.py:33-106 and
+    dec_grid.py:8-23 evaluated in float64."""
+    rng = _rng(13)
+    HW = H * W
+    x = (rng.random((B, 1, tw, H, W)) * 0.5 + 0.1).astype(np.float32)
+    delta = rng.standard_normal((B, 1, tw, H, W)).astype(np.float32)
+    mask = (rng.random((B, n_spatial, H, W)) < 0.2).astype(np.float32)
+    dt, pct = np.float32(0.01), np.float32(1 / 25)
+    steps = np.cumsum(np.full(tw, dt, dtype=np.float32), dtype=np.float32)
+    cap = np.cumsum(np.full(tw, pct, dtype=np.float32), dtype=np.float32)
+    out = be.empty((B, 1, tw, H, W))
+    d_delta, d_x, d_mask, d_steps, d_cap = (be.upload(a) for a in (delta, x, mask, steps, cap))     # keep the buffers alive
+    be.check(be.lib.pdes_constrain_forward(be.ptr(d_delta), be.ptr(d_x), be.ptr(d_mask), n_spatial * HW, be.ptr(d_steps),
+                                           be.ptr(d_cap), be.ptr(out), B, tw, HW, use_tanh, use_mask, use_volume, be.stream))
+    xd, dd, m = x.astype(np.float64), delta.astype(np.float64), mask[:, 0].astype(np.float64)[:, None, None]
+    u = xd[:, :, -1:] + steps.astype(np.float64)[None, None, :, None, None] * dd
+    if use_tanh:
+        u = np.tanh(u)
+    if use_mask:
+        u = u - m * u
+    if use_volume:
+        new = u.sum(axis=(3, 4))
+        prev = np.broadcast_to(xd[:, :, -1].sum(axis=(2, 3))[:, :, None], new.shape)
+        c = cap.astype(np.float64)[None, None, :]
+        dif = np.tanh((1 - new / prev) * 100 / c) / 100 * c
+        u = u / new[..., None, None] * ((1 - dif) * prev)[..., None, None]
+        if use_mask:
+            u = u - m * u
+    err = so.rel_l2(be.download(out), u)
+    assert err < TOL, f"constrain_forward tanh={use_tanh} mask={use_mask} volume={use_volume}: rel L2 {err:.3e}"
+    return err

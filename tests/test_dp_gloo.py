@@ -27,7 +27,8 @@ def _worker(rank, world, port, out_dir):
                 p.mul_(1.5)
     opt = torch.optim.SGD(model.parameters(), lr=0.0)
     tr = AutoregressivePushforwardTrainer(model, pde, optimizer=opt, device="cpu", batch_size=1, base_resolution=(501, 24, 16))
-    dp.make_data_parallel(tr, seed=42)
+    dp.make_data_parallel(tr, seed=42, bucket_mb=0.02)           # tiny buckets: several overlapped all-reduces per step
+    assert len(tr.grad_bucket.ranges) > 3
     u, labels, mask = (torch.from_numpy(g[k])[rank:rank + 1] for k in ("u", "labels", "mask"))
     pos = pde.x[None]
     with cpu_port():

@@ -147,3 +147,10 @@ def test_timeconv_decoder(be):
     kc.check_timeconv(be, B=2, HW=150, act=1)
     kc.check_timeconv(be, B=1, HW=128, act=0)
     kc.check_timeconv(be, B=4, HW=96 * 64, act=1)     # the decoder shape of the twophase config
+
+
+def test_fused_output_constraints(be):
+    kc.check_constrain(be)
+    kc.check_constrain(be, B=4, tw=25, H=96, W=64, n_spatial=1)
+    kc.check_constrain(be, B=2, tw=25, H=12, W=8, n_spatial=1, use_volume=0)
+    kc.check_constrain(be, B=1, tw=3, H=20, W=20, use_tanh=0, use_mask=0)

@@ -370,3 +370,24 @@ def test_conv1x1_falls_back_to_cudnn_when_unsupported():
     y = ops.conv1x1(x, conv)
     assert "Conv1x1" not in type(y.grad_fn).__name__
     assert rel_l2(y, conv(x)) == 0.0
+
+
+def test_fused_constraints_path_equals_module_path():
+    """No-grad applications take the fused add_delta + tanh + mask + volume-rescale kernel; it must reproduce the PyTorch
+    ops of ConstrainedSurrogate.forward (which the golden tests pin to the reference's activation_wrapper)."""
+    from neural_pde_surrogates_b200 import ops
+    model, pde, g = tiny_model(DEV)
+    model.eval()
+    B = g["u"].shape[0]
+    u, mask = (torch.from_numpy(g[k]).to(DEV) for k in ("u", "mask"))
+    pos = pde.x.to(DEV)[None].repeat(B, 1, 1, 1)
+    kw = dict(cond=torch.empty(B, 0, device=DEV), bc=None, pos=pos, t_cond=None, spatial_cond=mask)
+    with torch.no_grad():
+        fused = model(u, **kw)
+        ops.enable_fused_constraints = False
+        try:
+            plain = model(u, **kw)
+        finally:
+            ops.enable_fused_constraints = True
+    assert rel_l2(fused, plain) < 2e-6
+    assert rel_l2(model(u, **kw), g["y"]) < 1e-5          # grad mode: module path, pinned to the reference's output
