@@ -374,6 +374,8 @@ k_inv_w_gemm_tc_v3(TcParams p, int B, int ntiles_per_img, const __grid_constant_
   float* tsp = raw + (size_t)NRAW * slot_f;                     // [nsp_max*16][128]: fp32 A operand of the spectral chunks
   __shared__ __align__(8) V3RingBars bars;
   __shared__ uint32_t tmem_slot;
+  __shared__ __align__(16) float bias_s[kTcMaxN];      // the epilogue stalled on per-group __ldg(bias) (ncu: 18 % of all samples)
+  for (int i = threadIdx.x; i < kTcMaxN; i += blockDim.x) bias_s[i] = (p.bias != nullptr && i < p.N) ? __ldg(p.bias + i) : 0.0f;
 
   // warp index as a warp-uniform value: the single-issuer roles below run with the whole warp converged and one elected
   // lane issuing (ptx::*_ws), which keeps their operands in uniform registers (no waterfall loop per tcgen05 / TMA issue)
@@ -691,7 +693,6 @@ k_inv_w_gemm_tc_v3(TcParams p, int B, int ntiles_per_img, const __grid_constant_
       const uint32_t a = it & 1;
       const bool has_res = p.res != nullptr && pvalid;
       const bool has_pre = p.pre != nullptr, do_gelu = p.act == PDES_ACT_GELU;
-      const bool has_bias = p.bias != nullptr, bias_vec = aligned16(p.bias);
       // the residual (U-Net branch) is prefetched TWO column groups ahead: the epilogue is the pacing role of this kernel
       // and, with one group in flight per warp (16 KB per SM), it ran at the latency of its own loads (~2900 cycles per group)
       float cur[8], nxt[8], nx2[8];
@@ -740,16 +741,10 @@ k_inv_w_gemm_tc_v3(TcParams p, int B, int ntiles_per_img, const __grid_constant_
           float* const pq = p.pre;
           if (n0 + 8 <= N) {                                         // whole group valid: no per-element guards
             float bz[8];
-            if (has_bias && bias_vec) {
-              const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n0));
-              const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + 4));
+            {
+              const float4 b0 = *reinterpret_cast<const float4*>(bias_s + n0);          // warp-broadcast shared-memory loads
+              const float4 b1 = *reinterpret_cast<const float4*>(bias_s + n0 + 4);
               bz[0] = b0.x; bz[1] = b0.y; bz[2] = b0.z; bz[3] = b0.w; bz[4] = b1.x; bz[5] = b1.y; bz[6] = b1.z; bz[7] = b1.w;
-            } else if (has_bias) {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) bz[e] = __ldg(p.bias + n0 + e);
-            } else {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) bz[e] = 0.0f;
             }
 #pragma unroll
             for (int e = 0; e < 8; e += 2) {                         // two outputs per step: packed-FFMA2 GELU
@@ -764,7 +759,7 @@ k_inv_w_gemm_tc_v3(TcParams p, int B, int ntiles_per_img, const __grid_constant_
           } else {
             for (int e = 0; e < 8 && n0 + e < N; ++e) {
               float v = __uint_as_float(r[e]) + cur[e];
-              if (has_bias) v += __ldg(p.bias + n0 + e);
+              v += bias_s[n0 + e];
               if (has_pre) pq[o0 + (uint32_t)e * uHW] = v;
               if (do_gelu) v = gelu_fast_f(v);
               po[o0 + (uint32_t)e * uHW] = v;
