@@ -78,10 +78,9 @@ int pdes_mix_dw(const float* X, const float* GO, float* gw1, float* gw2,
  *                      when the parameters change (once per optimizer step; never during a rollout).  The parameters,
  *                      their gradients, Adam and the all-reduce keep the reference layout.
  *   pdes_dft_fwd2    : K1 that additionally writes the mode-major spectrum X2[m][b][i_pad] complex.
- *   pdes_mix_tc_fwd  : O2[2][m][b][o] complex = mix(X2, Wp); partial 1 is only written for the work items that were
- *                      split between two CTAs (the chunk stream is cut into equal ranges, one per SM).
- *   pdes_inv_h_modes : K3a for that layout: Z[b][h][2l+ri][o] = sum_k e^{+2 pi i kx_k h/H} (O2[0] + O2[1] where split);
- *                      `Cin` must be the reduction width pdes_mix_tc_fwd ran with.
+ *   pdes_mix_tc_fwd  : O2[2][m][b][o] complex = mix(X2, Wp); partial 1 holds the part of a work item that a second CTA
+ *                      finished (the chunk stream is cut into equal ranges, one per SM) and zeros otherwise.
+ *   pdes_inv_h_modes : K3a for that layout: Z[b][h][2l+ri][o] = sum_k e^{+2 pi i kx_k h/H} (O2[0] + O2[1]).
  * pdes_mix_tc_ok() == 0 (B > 32, tensor-core mode < 2, no TMA driver entry point) => use pdes_mix_fwd + pdes_inv_h. */
 int pdes_mix_tc_ok(int B, int Cin, int Cout, int m1, int m2);
 size_t pdes_mix_tc_pack_floats(int Cin, int Cout, int m1, int m2);
@@ -91,8 +90,7 @@ int pdes_mix_tc_pack(const float* w1, const float* w2, float* Wp, int Cin, int C
 int pdes_dft_fwd2(const float* x0, int C0, const float* x1, int C1, int B, int H, int W, int m1, int m2,
                   const float* tables, int herm_scale, float* X, float* X2, void* stream);
 int pdes_mix_tc_fwd(const float* X2, const float* Wp, float* O2, int B, int Cin, int Cout, int m1, int m2, void* stream);
-int pdes_inv_h_modes(const float* O2, int B, int Cin, int C, int H, int m1, int m2, const float* tables, float* Z,
-                     void* stream);
+int pdes_inv_h_modes(const float* O2, int B, int C, int H, int m1, int m2, const float* tables, float* Z, void* stream);
 
 /* ---- K3a: inverse DFT along H -----------------------------------------------------------------------
  * Z[b][h][j][c] (c fastest, j = 2*l + {re,im}) = sum_k e^{+2 pi i kx_k h/H} * sum_s P[s][b][c][k][l].

@@ -38,7 +38,7 @@ _PROTOTYPES = {
     "pdes_mix_tc_pack": (c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "pdes_dft_fwd2": (c_int, [_P, _I, _P, _I, _I, _I, _I, _I, _I, _P, _I, _P, _P, _P]),
     "pdes_mix_tc_fwd": (c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
-    "pdes_inv_h_modes": (c_int, [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
+    "pdes_inv_h_modes": (c_int, [_P, _I, _I, _I, _I, _I, _P, _P, _P]),
     "pdes_inv_h": (c_int, [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
     "pdes_inv_w_gemm": (c_int, [_P, _P, _I, _P, _I, _P, _I, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "pdes_set_tensor_core_mode": (None, [_I]),

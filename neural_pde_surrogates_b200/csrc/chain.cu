@@ -66,7 +66,7 @@ int pdes_block_forward(const float* h, int C0, const float* vb, int C1, const fl
     float* O2 = ws + w.O2;
     if (int e = pdes_dft_fwd2(h, C0, vb, C1, B, H, W, m1, m2, tables, 0, Xsave, X2, stream)) return e;
     if (int e = pdes_mix_tc_fwd(X2, wspec, O2, B, Cin, Cout, m1, m2, stream)) return e;
-    if (int e = pdes_inv_h_modes(O2, B, Cin, Cout, H, m1, m2, tables, Z, stream)) return e;
+    if (int e = pdes_inv_h_modes(O2, B, Cout, H, m1, m2, tables, Z, stream)) return e;
   } else {
     if (int e = pdes_dft_fwd(h, C0, vb, C1, B, H, W, m1, m2, tables, 0, Xsave, stream)) return e;
     if (int e = pdes_mix_fwd(Xsave, w1, w2, P, w.nsplit, B, Cin, Cout, H, m1, m2, stream)) return e;

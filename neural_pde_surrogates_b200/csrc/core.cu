@@ -83,6 +83,13 @@ int pdes_tables_fill(int H, int W, int m1, int m2, float* buf) {
       buf[t.twp + ((size_t)j * t.npp + pp) * 2] = (float)std::cos(a);
       buf[t.twp + ((size_t)j * t.npp + pp) * 2 + 1] = (float)std::sin(a);
     }
+  for (int l = 0; l < m2; ++l)
+    for (int w = 0; w < W; ++w) {
+      const long r = ((long)l * (long)w) % (long)W;
+      const double a = two_pi * (double)r / (double)W;
+      buf[t.tw2 + ((size_t)l * (W + 1) + w) * 2] = (float)std::cos(a);
+      buf[t.tw2 + ((size_t)l * (W + 1) + w) * 2 + 1] = (float)std::sin(a);
+    }
   for (int l = 0; l < m2; ++l) {
     double c = 2.0;
     if (l == 0) c = 1.0;

@@ -64,9 +64,11 @@ int mix_dw_tma_launch(const float* X, const float* GO, float* gw1, float* gw2, i
 // tinv_b [2*m2][W]     K3b backward: same with s_l = 1
 // herm   [m2]          s_l
 // twp    [m1+1][npp][2] K3a (v2): (cos, sin)(2 pi j p / H) for the folded row pairs p = 0 .. H/2 (npp = pairs rounded up to 8)
+// tw2    [m2][W+1][2]  K1 fast path stage 2: (cos, sin)(2 pi l w / W), row padded by one entry (bank spread)
+// (order in the blob: twh, twp, tw2, twa, tinv_f, tinv_b, herm)
 struct TableLayout {
   int nc4, npp;
-  size_t twh, twa, tinv_f, tinv_b, herm, twp, total;
+  size_t twh, twa, tinv_f, tinv_b, herm, twp, tw2, total;
 };
 __host__ __device__ inline size_t round4(size_t n) { return (n + 3) & ~size_t(3); }
 __host__ __device__ inline TableLayout table_layout(int H, int W, int m1, int m2) {
@@ -75,7 +77,8 @@ __host__ __device__ inline TableLayout table_layout(int H, int W, int m1, int m2
   t.npp = (H / 2 + 1 + 7) / 8 * 8;
   t.twh = 0;
   t.twp = t.twh + round4((size_t)2 * H);                       // (offsets of twh and twp do not depend on W)
-  t.twa = t.twp + round4((size_t)(m1 + 1) * t.npp * 2);
+  t.tw2 = t.twp + round4((size_t)(m1 + 1) * t.npp * 2);        // [m2][W+1] (cos, sin)(2 pi l w / W): K1 fast path, one bulk copy
+  t.twa = t.tw2 + round4((size_t)m2 * (W + 1) * 2);
   t.tinv_f = t.twa + (size_t)W * t.nc4;
   t.tinv_b = t.tinv_f + round4((size_t)2 * m2 * W);
   t.herm = t.tinv_b + round4((size_t)2 * m2 * W);

@@ -191,14 +191,14 @@ __device__ __forceinline__ void dft_fast_stage1(const float* __restrict__ col, f
 template <int H, int W, int M1, int M2>
 __global__ void __launch_bounds__(2 * W)
 k_dft_fwd_fast(const float* __restrict__ x0, int C0, const float* __restrict__ x1, int C1,
-               const float* __restrict__ twa_g, int nc4, const float* __restrict__ lscale, float* __restrict__ X,
-               float2* __restrict__ X2, int B, int CinP) {
+               const float* __restrict__ twa_g, int nc4, const float* __restrict__ tw2_g, const float* __restrict__ lscale,
+               float* __restrict__ X, float2* __restrict__ X2, int B, int CinP) {
   static_assert(H == 96, "twiddle table instantiated for H = 96");
   static_assert(H % 2 == 0 && 2 * M1 <= H && M2 <= W / 2 + 1, "fast path preconditions");
   constexpr int NK = M1 + 1;                 // |kx| = 0 .. M1
   __align__(128) __shared__ float img[H * W];
   __shared__ float pq[2][NK][W + 1];
-  __shared__ float2 tw2[M2][W + 1];
+  __align__(16) __shared__ float2 tw2[M2][W + 1];
   __align__(8) __shared__ unsigned long long mbar;
 
   const int tid = threadIdx.x;
@@ -211,18 +211,19 @@ k_dft_fwd_fast(const float* __restrict__ x0, int C0, const float* __restrict__ x
   if (tid == 0) {
     ptx::mbar_init(&mbar, 1);
     ptx::fence_mbar_init();
-    ptx::mbar_arrive_expect_tx(&mbar, H * W * 4);
+    // the stage-2 twiddle table arrives with the image: a second bulk copy on the same mbarrier (ncu: the per-thread
+    // __ldg fill of this table was 21 % of the kernel's stall samples, a dependent global-load phase in every CTA)
+    ptx::mbar_arrive_expect_tx(&mbar, H * W * 4 + M2 * (W + 1) * 8);
     ptx::bulk_g2s(img, src, H * W * 4, &mbar);
+    ptx::bulk_g2s(&tw2[0][0], tw2_g, M2 * (W + 1) * 8, &mbar);
   }
+  (void)twa_g; (void)nc4;
 #else
-  (void)mbar;
+  (void)mbar; (void)twa_g; (void)nc4;
   for (int i = tid; i < H * W; i += 2 * W) img[i] = src[i];
+  for (int i = tid; i < M2 * (W + 1) * 2; i += 2 * W) (&tw2[0][0].x)[i] = tw2_g[i];
 #endif
-  for (int i = tid; i < M2 * W; i += 2 * W) {
-    const int l = i / W, w = i % W;
-    tw2[l][w] = make_float2(__ldg(twa_g + w * nc4 + 2 * l), -__ldg(twa_g + w * nc4 + 2 * l + 1));
-  }
-  __syncthreads();                            // mbarrier init + tw2 visible to everyone
+  __syncthreads();                            // mbarrier init (and, emulated, the copies) visible to everyone
 #ifndef PDES_CPU_EMU
   ptx::mbar_wait(&mbar, 0);
 #endif
@@ -285,11 +286,11 @@ int dft_fwd_impl(const float* x0, int C0, const float* x1, int C1, int B, int H,
   PDES_REQUIRE(m1 > 0 && m2 > 0 && m1 <= H && m2 <= W / 2 + 1, PDES_ERR_ARG,
                "modes (%d,%d) exceed the grid (%d,%d): need m1 <= H and m2 <= W/2+1", m1, m2, H, W);
   const TableLayout t = table_layout(H, W, m1, m2);
-  if (H == 96 && W == 64 && m1 == 10 && m2 == 10 && aligned16(x0) && (x1 == nullptr || aligned16(x1))) {
+  if (H == 96 && W == 64 && m1 == 10 && m2 == 10 && aligned16(x0) && (x1 == nullptr || aligned16(x1)) && aligned16(tables)) {
     auto kfast = k_dft_fwd_fast<96, 64, 10, 10>;
     PDES_MAX_CARVEOUT(kfast);
     PDES_LAUNCH(kfast, dim3((unsigned)(B * (C0 + C1))), dim3(128), 0, stream, x0, C0, x1, C1, tables + t.twa, t.nc4,
-                herm_scale ? tables + t.herm : nullptr, X, X2, B, CinP);
+                tables + t.tw2, herm_scale ? tables + t.herm : nullptr, X, X2, B, CinP);
     return check_launch("pdes_dft_fwd(fast)");
   }
   const int xs_stride = (W % 2 == 0) ? W + 1 : W;

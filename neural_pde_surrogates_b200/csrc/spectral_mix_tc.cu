@@ -21,7 +21,8 @@
 //       gradient all-reduce keep the reference layout [Cin][Cout][m1][m2].
 //   X2  [m][b][i_pad] complex, mode-major copy of the retained spectrum written by K1 (pad columns are never read
 //       unmasked);
-//   O2  [2][m][b][o] complex: partial 0 and (for work items split between two CTAs) partial 1, summed by K3a.
+//   O2  [2][m][b][o] complex: partial 0 and partial 1 (the part of a work item that a second CTA finished; zero for the
+//       items that one CTA computed completely), summed by K3a.
 //
 // Work decomposition: an item = (mode m, tile of <= 128 output channels) = i_pad/16 chunks of 16 input channels; the
 // flattened chunk stream is cut into equal contiguous ranges, one per CTA (persistent, one CTA per SM), so the load
@@ -96,16 +97,11 @@ k_mix_tc_pack(const float2* __restrict__ w1, const float2* __restrict__ w2, floa
 }
 
 // ------------------------------------------------------------------------------------------------- K3a (v2)
-// Z[b][h][2l + {re,im}][o] = sum_k e^{+2 pi i kx_k h / H} (O2[0][m][b][o] + [item split] O2[1][m][b][o]),  m = k*m2 + l.
+// Z[b][h][2l + {re,im}][o] = sum_k e^{+2 pi i kx_k h / H} (O2[0][m][b][o] + O2[1][m][b][o]),  m = k*m2 + l.
 // CTA = (32 output channels, one l, one sample): lanes run along o (coalesced loads of O2 and stores of Z), the four
 // warps take the row pairs (h, H-h) round-robin.  A pair shares its four real sums:
 //     P = sum_k cos(t_k h) O_k,  Q = sum_k sin(t_k h) O_k  =>  z(h) = P + iQ,  z(H-h) = P - iQ,
 // which halves the multiplies for any (H, m1).  Twiddles come from a per-CTA shared table (warp-broadcast loads).
-struct SplitRule { int nck, per, ntile, to; };       // how K2 cut its chunk stream (to find the items with two partials)
-__device__ __forceinline__ bool item_is_split(const SplitRule& r, int item) {
-  return (item * r.nck) / r.per != ((item + 1) * r.nck - 1) / r.per;
-}
-
 // Rows +kx and -kx are folded as well: with S_j = O[kx=j] + O[kx=-j], D_j = O[kx=j] - O[kx=-j] (j = 0..m1; j = 0 has no
 // partner, j = m1 only the negative one) the sums run over m1 + 1 terms instead of 2*m1:
 //     P = sum_j cos(2 pi j h/H) S_j,  Q = sum_j sin(2 pi j h/H) D_j.
@@ -113,8 +109,10 @@ __device__ __forceinline__ bool item_is_split(const SplitRule& r, int item) {
 // feed 32 FMAs.
 constexpr int kIh2HP = 8;                                // row pairs per thread
 constexpr int kIh2MaxWarps = 16;
+// (A persistent, cp.async double-buffered variant of this kernel was measured on B200 and was not faster -- 23.0 vs
+// 20.5 us in the cold-cache ncu pass -- so the simple one-CTA-per-item form stays.)
 __global__ void __launch_bounds__(32 * kIh2MaxWarps)
-k_inv_h2(const float2* __restrict__ O2, SplitRule rule, int B, int C, int H, int m1, int m2,
+k_inv_h2(const float2* __restrict__ O2, int B, int C, int H, int m1, int m2,
          const float2* __restrict__ twp_g, float* __restrict__ Z) {
   PDES_DYN_SMEM(float2, sm2);
   const int K = 2 * m1, M2 = K * m2, J = 2 * m2, NJ = m1 + 1;
@@ -126,42 +124,23 @@ k_inv_h2(const float2* __restrict__ O2, SplitRule rule, int B, int C, int H, int
   const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, wq = tid >> 5, nwarp = nthr >> 5;
   const int o0 = blockIdx.x * 32, l = blockIdx.y, b = blockIdx.z;
   const int o = o0 + lane;
-  __shared__ unsigned char split_s[2 * 64 + 2];        // [k]: row k of this block's channel tiles carries a second partial
+  // every global load of the block is issued before its one barrier
   for (int idx = tid; idx < NJ * npp; idx += nthr) tw[idx] = __ldg(twp_g + idx);     // host-built table, coalesced
-  // the 32 channels of a block lie in at most two output-channel tiles of K2: flags for both
-  const int t_lo = o0 / rule.to, t_hi = (o0 + 31 < C ? o0 + 31 : C - 1) / rule.to;
-  for (int k = tid; k < K; k += nthr) {
-    const int m = k * m2 + l;
-    unsigned char f = 0;
-    if (item_is_split(rule, m * rule.ntile + t_lo)) f |= 1;
-    if (item_is_split(rule, m * rule.ntile + t_hi)) f |= 2;
-    if (k < 2 * 64) split_s[k] = f;
-  }
-  __syncthreads();
-  const int o_hi0 = (t_lo + 1) * rule.to;              // first channel of the upper tile
   const size_t pstride = (size_t)M2 * B * C;
-  auto load_o = [&](int k, int oo) -> float2 {         // O[k][l] of channel oo (both partials where the item was split)
+  auto load_o = [&](int k, int oo) -> float2 {         // O[k][l] of channel oo = partial 0 + partial 1 (zero unless split)
     const size_t at = ((size_t)(k * m2 + l) * B + b) * C + oo;
-    float2 v = __ldg(O2 + at);
-    const unsigned char f = (k < 2 * 64) ? split_s[k] : (unsigned char)(item_is_split(rule, (k * m2 + l) * rule.ntile + oo / rule.to) ? 3 : 0);
-    if (f & (oo >= o_hi0 ? 2 : 1)) {
-      const float2 u = __ldg(O2 + pstride + at);
-      v.x += u.x; v.y += u.y;
-    }
-    return v;
+    const float2 v = __ldg(O2 + at), u = __ldg(O2 + pstride + at);
+    return make_float2(v.x + u.x, v.y + u.y);
   };
   for (int idx = tid; idx < NJ * 32; idx += nthr) {
     const int j = idx >> 5, oo = o0 + (idx & 31);
     float2 sv = make_float2(0.f, 0.f), dv = make_float2(0.f, 0.f);
     if (oo < C) {
-      if (j < m1) {                                    // +kx = j lives in row k = j
-        const float2 a = load_o(j, oo);
-        sv = a; dv = a;
-      }
-      if (j > 0) {                                     // -kx = -j lives in row k = 2*m1 - j
-        const float2 c = load_o(K - j, oo);
-        sv.x += c.x; sv.y += c.y; dv.x -= c.x; dv.y -= c.y;
-      }
+      float2 a = make_float2(0.f, 0.f), c = make_float2(0.f, 0.f);
+      if (j < m1) a = load_o(j, oo);                   // +kx = j lives in row k = j
+      if (j > 0) c = load_o(K - j, oo);                // -kx = -j lives in row k = 2*m1 - j
+      sv = make_float2(a.x + c.x, a.y + c.y);
+      dv = make_float2(a.x - c.x, a.y - c.y);
     }
     Ss[idx] = sv;
     Ds[idx] = dv;
@@ -184,16 +163,18 @@ k_inv_h2(const float2* __restrict__ O2, SplitRule rule, int B, int C, int H, int
       }
     }
     if (o < C) {
+      float* const zb = Z + ((size_t)b * H * J + 2 * l) * C + o;          // row h of this (sample, l, channel): zb + h * J * C
+      const size_t rs = (size_t)J * C;
 #pragma unroll
       for (int e = 0; e < kIh2HP; ++e) {
         const int h = p0 + e;
         if (h < npair) {
-          float* z = Z + (((size_t)b * H + h) * J + 2 * l) * C + o;
+          float* z = zb + (size_t)h * rs;
           z[0] = pr[e] - qi[e];                                           // Re (P + iQ)
           z[C] = pi[e] + qr[e];
           const int h2 = H - h;
-          if (h != 0 && h2 != h && h2 < H) {
-            float* z2 = Z + (((size_t)b * H + h2) * J + 2 * l) * C + o;
+          if (h != 0 && h2 != h) {
+            float* z2 = zb + (size_t)h2 * rs;
             z2[0] = pr[e] + qi[e];                                        // Re (P - iQ)
             z2[C] = pi[e] - qr[e];
           }
@@ -453,6 +434,8 @@ k_mix_tc(MtParams p, const __grid_constant__ CUtensorMap tmap_w, const __grid_co
       ptx::tc_fence_after();
       const uint32_t tb = tmem_base + ((uint32_t)(quad * 32) << 16) + a * 4u * (uint32_t)npad;
       float2* dst = p.O2 + (kc0 != 0 ? pstride : 0) + ((size_t)m * p.B) * p.Cout + o;   // partial 1 = continuation of a split item
+      // a part that covers its whole item also zeroes partial 1, so K3a adds the two partials unconditionally
+      float2* zero1 = (kc0 == 0 && cl - c == p.nck) ? dst + pstride : nullptr;
       // accumulator q received the chunks g = q (mod 4) of this part; a part shorter than 4 chunks leaves some untouched
       const int g0 = c - c_beg, nch_part = cl - c;
       bool used[4];
@@ -485,6 +468,7 @@ k_mix_tc(MtParams p, const __grid_constant__ CUtensorMap tmap_w, const __grid_co
               const float re = (__uint_as_float(v2[e]) + __uint_as_float(v3[e])) + (__uint_as_float(v1[e]) + __uint_as_float(v0[e]));
               const float im = (__uint_as_float(v2[e + 1]) + __uint_as_float(v3[e + 1])) + (__uint_as_float(v1[e + 1]) + __uint_as_float(v0[e + 1]));
               dst[(size_t)bb * p.Cout] = make_float2(re, im);
+              if (zero1 != nullptr) zero1[(size_t)bb * p.Cout] = make_float2(0.f, 0.f);
             }
           }
         }
@@ -653,28 +637,23 @@ int pdes_mix_tc_fwd(const float* X2, const float* Wp, float* O2, int B, int Cin,
 #endif
 }
 
-/* K3a for the layout K2-on-tcgen05 writes: Z[b][h][2l+ri][c] from O2 (two partials, see pdes_mix_tc_fwd).  `Cin` is
- * the reduction width K2 ran with (it fixes which items carry a second partial). */
-int pdes_inv_h_modes(const float* O2, int B, int Cin, int C, int H, int m1, int m2, const float* tables, float* Z,
-                     void* stream) {
+/* K3a for the layout K2-on-tcgen05 writes: Z[b][h][2l+ri][c] from O2 (two partials, see pdes_mix_tc_fwd). */
+int pdes_inv_h_modes(const float* O2, int B, int C, int H, int m1, int m2, const float* tables, float* Z, void* stream) {
   using namespace pdes;
   PDES_REQUIRE(O2 && tables && Z, PDES_ERR_ARG, "pdes_inv_h_modes: null pointer");
-  PDES_REQUIRE(B > 0 && C > 0 && H > 0 && m1 > 0 && m2 > 0 && m1 <= H && Cin > 0, PDES_ERR_ARG, "pdes_inv_h_modes: bad sizes");
-  PDES_REQUIRE(B <= 65535 && m2 <= 65535, PDES_ERR_UNSUPPORTED, "pdes_inv_h_modes: grid too large");
-  const MtGeom g = mt_geom(B, Cin, C, m1, m2, mt_sms());
-  SplitRule rule;
-  rule.nck = g.nck; rule.per = g.per; rule.ntile = g.ntile; rule.to = g.to;
+  PDES_REQUIRE(B > 0 && C > 0 && H > 0 && m1 > 0 && m2 > 0 && m1 <= H, PDES_ERR_ARG, "pdes_inv_h_modes: bad sizes");
   const int npair = H / 2 + 1, npp = ceil_div(npair, kIh2HP) * kIh2HP;
   const size_t smem = ((size_t)2 * (m1 + 1) * 32 + (size_t)(m1 + 1) * npp) * sizeof(float2);
   PDES_REQUIRE(smem <= (size_t)kMaxDynSmem && (long)H * m1 < (1L << 31), PDES_ERR_UNSUPPORTED,
                "pdes_inv_h_modes: needs %zu B of shared memory", smem);
+  PDES_REQUIRE(B <= 65535 && m2 <= 65535, PDES_ERR_UNSUPPORTED, "pdes_inv_h_modes: grid too large");
   int nwarp = ceil_div(npair, kIh2HP);
   if (nwarp > kIh2MaxWarps) nwarp = kIh2MaxWarps;
   auto kfn = k_inv_h2;
   if (smem > 48 * 1024) PDES_SET_SMEM(kfn, smem);
   PDES_MAX_CARVEOUT(kfn);
   PDES_LAUNCH(kfn, dim3((unsigned)ceil_div(C, 32), (unsigned)m2, (unsigned)B), dim3((unsigned)(32 * nwarp)), smem, stream,
-              reinterpret_cast<const float2*>(O2), rule, B, C, H, m1, m2,
+              reinterpret_cast<const float2*>(O2), B, C, H, m1, m2,
               reinterpret_cast<const float2*>(tables + table_layout(H, 2, m1, m2).twp), Z);
   return check_launch("pdes_inv_h_modes");
 }

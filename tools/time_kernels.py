@@ -90,7 +90,7 @@ def main():
                                       4 * B * Cin * HW + 16 * B * Cin * 2 * MM),
             "K2_mix_tcgen05": (lambda: ck(lib.pdes_mix_tc_fwd(p(X2), p(wsp), p(O2), B, Cin, Cout, m1, m2, st)),
                                16 * Cin * Cout * MM + 8 * B * Cin * 2 * MM + 8 * B * Cout * 2 * MM),
-            "K3a_inv_h_modes": (lambda: ck(lib.pdes_inv_h_modes(p(O2), B, Cin, Cout, H, m1, m2, p(tab), p(Z), st)),
+            "K3a_inv_h_modes": (lambda: ck(lib.pdes_inv_h_modes(p(O2), B, Cout, H, m1, m2, p(tab), p(Z), st)),
                                 8 * B * Cout * 2 * MM + 4 * B * H * 2 * m2 * Cout),
             "spectral_weight_pack": (lambda: ck(lib.pdes_mix_tc_pack(p(w1), p(w2), p(wsp), Cin, Cout, H, m1, m2, st)),
                                      32 * Cin * Cout * MM),
