@@ -264,6 +264,60 @@ class AutoregressivePushforwardTrainer:
             self.grad_sync()
         self.optimizer.step()
 
+    # ------------------------------------------------------------------------------------------ epoch loop
+    def train_one_epoch(self, loader, epoch: int, lr_scheduler=None, max_train_batches=float("inf")):
+        """One pass over `loader` (batches of whole trajectories, as PDE2DDataset yields them): H2D, zero_grad ->
+        train_step -> backward -> [gradient all-reduce] -> step, loss accounting and the lr schedule exactly as
+        TrainInterface.train_one_epoch (trainers/base.py:472-507; the batch-limit check comes AFTER the step, :498)."""
+        self.model.train()
+        dev = self.config.device
+        total = 0
+        for batch_idx, batch in enumerate(loader):
+            batch = tuple(t.to(dev, non_blocking=True) if isinstance(t, torch.Tensor) else t for t in batch)
+            loss, _ = self.train_step(batch, epoch, batch_idx, loader=loader)
+            self.optimizer_step(loss)
+            total = total + loss.detach() / batch[1].shape[0]                  # utils.get_batch_size
+            if batch_idx >= max_train_batches:
+                break
+        total = total / len(loader)
+        if lr_scheduler is not None and (epoch + 1) % self.config.lr_step_interval == 0:   # :504-506
+            lr_scheduler.step()
+        return total
+
+    def train(self, train_loader, num_epochs: int, valid_loader=None, test_interval: int = 25, lr_scheduler=None,
+              save_path: Optional[str] = None, max_train_batches=float("inf")):
+        """Epoch loop of TrainInterface.train (trainers/base.py:219-347) without the logging / W&B plumbing: training
+        epochs, validation with test_step every `test_interval` epochs, best / final checkpoints with the reference's
+        state_dict keys (`torch.save(model.state_dict())`, :349-355).  Returns (train_losses, val_losses)."""
+        train_losses, val_losses, best = [], [], float("inf")
+        for epoch in range(num_epochs):
+            train_losses.append(self.train_one_epoch(train_loader, epoch, lr_scheduler, max_train_batches))
+            if valid_loader is not None and (epoch + 1) % test_interval == 0:
+                val = self.test(valid_loader)
+                val_losses.append(val)
+                if save_path is not None and float(val) < best:
+                    best = float(val)
+                    self.save_model(save_path + "_unrolled.pt")
+        if save_path is not None:
+            self.save_model(save_path + "_final.pt")
+        return train_losses, val_losses
+
+    def test(self, loader, max_test_batches=float("inf")):
+        """Mean of test_step's primary loss over the loader (trainers/base.py:378-470, grid path)."""
+        self.model.eval()
+        dev = self.config.device
+        losses = []
+        with torch.no_grad():
+            for batch_idx, batch in enumerate(loader):
+                batch = tuple(t.to(dev) if isinstance(t, torch.Tensor) else t for t in batch)
+                losses.append(self.test_step(batch, batch_idx)[0])
+                if batch_idx >= max_test_batches:
+                    break
+        return torch.mean(torch.stack(losses))
+
+    def save_model(self, path: str):
+        torch.save(self.model.state_dict(), path)                              # trainers/base.py:349-355
+
     # ------------------------------------------------------------------------------------------ rollout
     def graphed_train_step(self, data, labels, x, conditioning, spatial_conditioning, unrolled: int = 0):
         """The CUDA-graph version of train_step_windows + optimizer_step for these shapes (built on first use)."""

@@ -35,3 +35,31 @@ def test_create_data_distinct_steps_and_truncated_batch():
         dc.create_data(u, [3])                                  # step - tw < 0
     with pytest.raises(AssertionError):
         dc.create_data(u, [38])                                 # step + tw > T
+
+
+def test_epoch_loop_schedule_and_checkpoint(tmp_path):
+    """train_one_epoch / train / test / save_model (trainers/base.py:219-347,472-507): batch-limit semantics (the check
+    comes after the step), lr schedule every lr_step_interval epochs, checkpoints loadable with the same keys."""
+    from parity_util import tiny_model
+    from neural_pde_surrogates_b200.trainer import AutoregressivePushforwardTrainer
+    model, pde, g = tiny_model("cpu")
+    T = 100
+    torch.manual_seed(0)
+    u = torch.rand(4, 1, T, 24, 16) * 0.5 + 0.1
+    mask = (torch.rand(4, 1, 24, 16) < 0.1).float()
+    pos = pde.x[None].repeat(4, 1, 1, 1)
+    ds = [(torch.empty(0), u[i], pos[i], torch.empty(0), torch.empty(0), mask[i]) for i in range(4)]
+    loader = torch.utils.data.DataLoader(ds, batch_size=2, shuffle=False)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    sched = torch.optim.lr_scheduler.MultiStepLR(opt, milestones=[1, 2], gamma=0.4)
+    tr = AutoregressivePushforwardTrainer(model, pde, optimizer=opt, device="cpu", batch_size=2, base_resolution=(T, 24, 16),
+                                          lr_step_interval=1)
+    before = {k: v.clone() for k, v in model.state_dict().items()}
+    with cpu_port():
+        tl, vl = tr.train(loader, num_epochs=2, valid_loader=loader, test_interval=2, lr_scheduler=sched,
+                          save_path=str(tmp_path / "ckpt"), max_train_batches=0)         # still trains ONE batch per epoch
+    assert len(tl) == 2 and len(vl) == 1 and all(torch.isfinite(x) for x in tl + vl)
+    assert abs(opt.param_groups[0]["lr"] - 1e-3 * 0.4 * 0.4) < 1e-12                     # stepped after epochs 0 and 1
+    sd = torch.load(tmp_path / "ckpt_final.pt")
+    assert list(sd) == list(before) and (tmp_path / "ckpt_unrolled.pt").exists()
+    assert any(not torch.equal(sd[k], before[k]) for k in sd)
