@@ -218,6 +218,14 @@ __device__ __forceinline__ void tma_load_3d_ws(void* dst, const void* tmap, int 
       "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
       : "memory");
 }
+// L2 prefetch of a 2-D tensor-map box (no shared memory, no completion tracking): one elected lane issues
+__device__ __forceinline__ void tma_prefetch_2d_ws(const void* tmap, int c0, int c1) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];\n\t}" ::"l"(tmap), "r"(c0), "r"(c1)
+      : "memory");
+}
 // warp index as a value the compiler knows to be warp-uniform
 __device__ __forceinline__ int uniform_warp_idx() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
 
