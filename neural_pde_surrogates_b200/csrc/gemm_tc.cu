@@ -359,7 +359,7 @@ constexpr int kV3TaMaxN = 208;
 template <bool kTA>
 __global__ void __launch_bounds__(kK3Threads, 1)
 k_inv_w_gemm_tc_v3(TcParams p, int B, int ntiles_per_img, const __grid_constant__ CUtensorMap tmap_x0, int ntmap_chunks,
-                   int NST, int NRAW, const __grid_constant__ CUtensorMap tmap_res, int res_prefetch) {
+                   int NST, int NRAW) {
   PDES_DYN_SMEM(unsigned char, smem_raw);
   unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int npad = p.npad;
@@ -430,13 +430,25 @@ k_inv_w_gemm_tc_v3(TcParams p, int B, int ntiles_per_img, const __grid_constant_
     // tile's rows).  It depends on the tile only through p0 % W, so when every tile starts at column 0
     // (128 % W == 0, e.g. the shipped W = 64) it is built ONCE per CTA; otherwise it is rebuilt per tile.
     const bool uniform_geom = (kTcM % W == 0);
+    // (counters instead of k / J and loads batched four at a time: as a division + dependent __ldg per k this table
+    // took ~11 k cycles = 5.6 us before the first chunk of the kernel could be converted)
     auto build_tsp = [&](int p0, int h0, int kspec, int nsp) {
       const int pp = p0 + tid;
       const bool pv = pp < HW;
       const int hh = pv ? pp / W : 0, ww = pv ? pp % W : 0;
-      for (int k = 0; k < nsp * kTcBK; ++k) {
-        const int rr = k / J, j = k - rr * J;
-        tsp[k * kTcM + tid] = (pv && k < kspec && hh - h0 == rr) ? __ldg(p.T + (size_t)j * W + ww) : 0.0f;
+      const int myr = pv ? hh - h0 : -1;                             // the one row block in which this pixel has non-zeros
+      const int kend = nsp * kTcBK;
+      for (int k = 0; k < kend; ++k) tsp[k * kTcM + tid] = 0.0f;
+      if (myr >= 0 && myr * J < kspec) {
+        const float* tcol = p.T + ww;
+        float* dst = tsp + (size_t)(myr * J) * kTcM + tid;
+        int j = 0;
+        for (; j + 4 <= J; j += 4) {
+          const float v0 = __ldg(tcol + (size_t)j * W), v1 = __ldg(tcol + (size_t)(j + 1) * W);
+          const float v2 = __ldg(tcol + (size_t)(j + 2) * W), v3 = __ldg(tcol + (size_t)(j + 3) * W);
+          dst[j * kTcM] = v0; dst[(j + 1) * kTcM] = v1; dst[(j + 2) * kTcM] = v2; dst[(j + 3) * kTcM] = v3;
+        }
+        for (; j < J; ++j) dst[j * kTcM] = __ldg(tcol + (size_t)j * W);
       }
     };
     if (p.Z != nullptr && uniform_geom && (int)blockIdx.x < ntiles) {
@@ -614,10 +626,8 @@ k_inv_w_gemm_tc_v3(TcParams p, int B, int ntiles_per_img, const __grid_constant_
         int b, p0, h0, kspec, nsp;
         tile_geom(t, b, p0, h0, kspec, nsp);
         const int npx = (HW - p0 < kTcM) ? (HW - p0) : kTcM;
-        // the epilogue of this tile runs one main loop (~8 us) from now: pull its U-Net residual tile [N][128 px] into
-        // L2 with ONE TMA prefetch, so the epilogue's loads see L2 latency instead of HBM latency (it is the pacing
-        // role and has no registers left for a deeper prefetch of its own)
-        if (res_prefetch) ptx::tma_prefetch_2d_ws(&tmap_res, p0, b * p.N);
+        // (a TMA L2 prefetch of this tile's residual [N][128 px], issued here, was measured on B200: 72.3 -> 77.2 us, like
+        // round 1's prefetch by an idle warp -- the epilogue is not waiting on HBM latency alone; removed)
         for (int c = 0; c < nsp + nx; ++c, ++g) {
           TRACE(2 * 512 + g * 4 + 0);
           if (g >= (uint32_t)NRAW) ptx::mbar_wait(&bars.raw_empty[r], rph);
@@ -1544,24 +1554,10 @@ int inv_w_gemm_tc_impl(const float* Z, const float* wpack, const float* x0, int 
 #define v3_nst v3_nst_used
 #define v3_nraw v3_nraw_used
 #endif
-    // tensor map over the residual [B*N rows][HW] for the per-tile L2 prefetch (contiguous batches only)
-    alignas(64) CUtensorMap tmap_res;
-    memset(&tmap_res, 0, sizeof(tmap_res));
-    int res_prefetch = 0;
-    if (res != nullptr && out_bs == (size_t)N * H * W && (H * W) % 4 == 0 && aligned16(res) && g_encode_tiled() != nullptr) {
-      const cuuint64_t gdim[2] = {(cuuint64_t)(H * W), (cuuint64_t)B * (cuuint64_t)N};
-      const cuuint64_t gstr[1] = {(cuuint64_t)(H * W) * 4};
-      const cuuint32_t box[2] = {(cuuint32_t)kTcM, (cuuint32_t)N};
-      const cuuint32_t estr[2] = {1, 1};
-      const CUresult r = g_encode_tiled()(&tmap_res, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(res), gdim, gstr,
-                                          box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-      if (r == CUDA_SUCCESS) res_prefetch = 1;
-    }
     auto k3 = v3_ta ? k_inv_w_gemm_tc_v3<true> : k_inv_w_gemm_tc_v3<false>;
     PDES_SET_SMEM(k3, smem3);
     PDES_LAUNCH(k3, dim3((unsigned)(ntiles < g_num_sms ? ntiles : g_num_sms)), dim3(kK3Threads), smem3, stream, p, B,
-                tiles_per_img, tmap, ntmap_chunks, v3_nst, v3_nraw, tmap_res, res_prefetch);
+                tiles_per_img, tmap, ntmap_chunks, v3_nst, v3_nraw);
 #ifdef PDES_TC_TRACE
 #undef v3_nst
 #undef v3_nraw
