@@ -93,7 +93,7 @@ constexpr int kTcThreads = 192;    // warps 0-3: convert + epilogue, warp 4: MMA
 __global__ void __launch_bounds__(kTcThreads, 2)
 k_inv_w_gemm_tc(TcParams p) {
   PDES_DYN_SMEM(unsigned char, smem_raw);
-  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* base = ptx::align_smem_1024(smem_raw);
   const int npad = p.npad;
   const uint32_t a_blk = kTcM * kTcBK * 4;                 // 8 KB
   const uint32_t b_blk = (uint32_t)npad * kTcBK * 4;
@@ -148,6 +148,7 @@ k_inv_w_gemm_tc(TcParams p) {
       if (c >= 2) ptx::mbar_wait(&empty_bar[s], (uint32_t)((u - 1) & 1));
       unsigned char* st = base + (size_t)s * stage_bytes;
       float v[kTcBK];
+      int release_slot = -1;
       if (c >= nsp) {
         const int cx = c - nsp;                               // activation chunk index
         if (tid == 0) {
@@ -159,7 +160,7 @@ k_inv_w_gemm_tc(TcParams p) {
         const float* rw = raw + (size_t)slot * kTcBK * kTcM + tid;
 #pragma unroll
         for (int kk = 0; kk < kTcBK; ++kk) v[kk] = (pvalid && cx * kTcBK + kk < p.K) ? rw[kk * kTcM] : 0.0f;
-        ptx::mbar_arrive(&raw_empty[slot]);
+        release_slot = slot;                                  // released below, once the loaded values have been consumed
       } else {
         const int cs = c;                                     // spectral chunks come first: their L2 latency
                                                               // overlaps the first bulk copies of the activations
@@ -209,6 +210,10 @@ k_inv_w_gemm_tc(TcParams p) {
         *reinterpret_cast<float4*>(st + off) = hi;
         *reinterpret_cast<float4*>(st + a_blk + off) = lo;
       }
+      // The raw slot is handed back only AFTER its values went through the stores above: an arrive placed right behind
+      // the loads is issued while they are still in flight (ptxas puts no scoreboard wait in front of SYNCS.ARRIVE), and
+      // the producer's next copy into the slot then overtakes them.
+      if (release_slot >= 0) ptx::mbar_arrive(&raw_empty[release_slot]);
       ptx::fence_proxy_async();
       ptx::mbar_arrive(&full_bar[s]);
     }
@@ -361,7 +366,7 @@ __global__ void __launch_bounds__(kK3Threads, 1)
 k_inv_w_gemm_tc_v3(TcParams p, int B, int ntiles_per_img, const __grid_constant__ CUtensorMap tmap_x0, int ntmap_chunks,
                    int NST, int NRAW) {
   PDES_DYN_SMEM(unsigned char, smem_raw);
-  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* base = ptx::align_smem_1024(smem_raw);
   const int npad = p.npad;
   const uint32_t a_blk = kTcM * kTcBK * 4;                       // 8 KB
   const uint32_t b_blk = (uint32_t)npad * kTcBK * 4;             // 12 KB at N = 192
@@ -474,6 +479,7 @@ k_inv_w_gemm_tc_v3(TcParams p, int B, int ntiles_per_img, const __grid_constant_
         if (tid == 0) TRACE(0 * 512 + g * 4 + 1);
         unsigned char* st = sA + s * a_stage;
         float v[kTcBK];
+        bool release_raw = false;
         if (kTA) ptx::tc_fence_after();
         if (c >= nsp) {
           const int cx = c - nsp;
@@ -482,8 +488,11 @@ k_inv_w_gemm_tc_v3(TcParams p, int B, int ntiles_per_img, const __grid_constant_
           const float* rw = raw + (size_t)r * slot_f + tid;               // activation rows: dense [16][128]
 #pragma unroll
           for (int kk = 0; kk < kTcBK; ++kk) v[kk] = (pvalid && cx * kTcBK + kk < p.K && !(dbg & 8)) ? rw[kk * kTcM] : 0.0f;
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(&bars.raw_empty[r]);
+          // raw_empty[r] is arrived on BELOW, after v[] went through tcgen05.st / st.shared.  Arriving here released
+          // the slot with the 16 loads still in flight (SASS: LD x16, SYNCS.ARRIVE, first use of the data after it); at
+          // B = 16 the producer's next TMA box overtook the last rows in ~1 of 8000 tiles (one k-row of a 32-pixel
+          // quadrant taken from the chunk 8 ahead): found by tools/stress_k3b.py.
+          release_raw = true;
         } else {
           // spectral chunk: A = T[j][w] on this pixel's row, B = Z rows (staged in the raw slot) -> canonical
 #pragma unroll
@@ -528,6 +537,10 @@ k_inv_w_gemm_tc_v3(TcParams p, int B, int ntiles_per_img, const __grid_constant_
           ptx::tmem_st16(trow + ta_hi, uh);
           ptx::tmem_st16(trow + ta_lo, ul);
           ptx::tmem_st_wait();
+          if (release_raw) {
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&bars.raw_empty[r]);
+          }
           ptx::tc_fence_before();
           if (c < nsp) ptx::fence_proxy_async();                     // the spectral B block went through st.shared
         } else {
@@ -541,6 +554,10 @@ k_inv_w_gemm_tc_v3(TcParams p, int B, int ntiles_per_img, const __grid_constant_
             const uint32_t off = (uint32_t)qd * (kTcM / 8) * 128 + row_off;
             *reinterpret_cast<float4*>(st + off) = hi;
             *reinterpret_cast<float4*>(st + a_blk + off) = lo;
+          }
+          if (release_raw) {
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&bars.raw_empty[r]);
           }
           ptx::fence_proxy_async();
         }
@@ -823,7 +840,7 @@ struct WgtParams {
 __global__ void __launch_bounds__(kWgtThreads, 1)
 k_wgrad_tc(WgtParams p, const __grid_constant__ CUtensorMap tmap_g, const __grid_constant__ CUtensorMap tmap_x0) {
   PDES_DYN_SMEM(unsigned char, smem_raw);
-  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* base = ptx::align_smem_1024(smem_raw);
   const uint32_t lbo_a = (uint32_t)(p.mrows / 8) * 128 + 32, lbo_b = (uint32_t)(p.npadN / 8) * 128 + 32;
   const uint32_t a_blk = 4 * lbo_a, b_blk = 4 * lbo_b;
   const uint32_t stage_bytes = 2 * a_blk + 2 * b_blk;
@@ -1027,7 +1044,7 @@ k_pack_conv3x3_tf32(const float* __restrict__ Wt, int N, int Cin, int npad, int 
 __global__ void __launch_bounds__(kV3Threads, 1)
 k_conv3x3_tc(ConvParams p, const __grid_constant__ CUtensorMap tmap_x) {
   PDES_DYN_SMEM(unsigned char, smem_raw);
-  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* base = ptx::align_smem_1024(smem_raw);
   const int npad = p.npad;
   const uint32_t a_blk = kTcM * kTcBK * 4;
   const uint32_t b_blk = (uint32_t)npad * kTcBK * 4;

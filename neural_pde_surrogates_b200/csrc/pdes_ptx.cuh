@@ -17,6 +17,11 @@ __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier
 // make generic-proxy shared-memory writes visible to the async proxy (TMA / tcgen05 operand reads)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// 1 KB alignment of the dynamic shared-memory window by POINTER arithmetic: rounding through uintptr_t loses the shared
+// address space and every later access through the result compiles to a generic LD.E / ST.E instead of LDS / STS.
+__device__ __forceinline__ unsigned char* align_smem_1024(unsigned char* p) {
+  return p + ((1024u - (smem_u32(p) & 1023u)) & 1023u);
+}
 __device__ __forceinline__ void mbar_arrive(void* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }

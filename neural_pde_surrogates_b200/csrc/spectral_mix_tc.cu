@@ -237,7 +237,7 @@ __device__ __forceinline__ uint64_t mt_desc_sw128(uint32_t saddr) {
 __global__ void __launch_bounds__(kMtThreads, 1)
 k_mix_tc(MtParams p, const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x) {
   PDES_DYN_SMEM(unsigned char, smem_raw);
-  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* base = ptx::align_smem_1024(smem_raw);
   const int npad = p.npad;
   const uint32_t lbo = (uint32_t)(npad / 8) * 128u + 16u;                  // +16: the k-quads of a row fall in different banks
   const uint32_t blk = 8u * lbo;                                           // one canonical [npad x 32] block (8 k-quads)
