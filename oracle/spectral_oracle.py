@@ -7,8 +7,9 @@ checker for the CUDA kernels; it is never imported by the product package
 
 Parity pin: the reference ships no tests or golden vectors, so this oracle
 is pinned by (i) `tests/golden/*.npz`, produced by *executing the reference modules* in the
-build container (`tests/golden/make_golden.py`), and (ii) `tests/test_oracle_vs_reference.py`
-which imports the reference live when `/root/reference` exists.
+build container (`tests/golden/make_golden.py`; checked by `tests/test_oracle_golden.py`), and (ii)
+`tests/test_oracle_vs_reference.py`, which imports the reference live (from `/root/reference/src` or the verbatim copy
+in `oracle/_ref/src`, see `oracle/reference_loader.py`) and compares on freshly drawn inputs.
 
 Reference lines restated here (paths relative to /root/reference/src):
   * models/enc_proc_dec_components/proc_fno.py:257-288  SpectralConv2d.forward

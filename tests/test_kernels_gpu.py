@@ -154,3 +154,33 @@ def test_fused_output_constraints(be):
     kc.check_constrain(be, B=4, tw=25, H=96, W=64, n_spatial=1)
     kc.check_constrain(be, B=2, tw=25, H=12, W=8, n_spatial=1, use_volume=0)
     kc.check_constrain(be, B=1, tw=3, H=20, W=20, use_tanh=0, use_mask=0)
+
+
+def test_tc_inverse_gemm_run_to_run_bitwise(be):
+    """The bench-shape K3b launch repeated 150 times must be bit-identical.  Before the raw-ring release was moved behind
+    the consumption of the loaded rows, ~9 % of B = 16 launches had one 32-pixel quadrant of one tile computed with a
+    k-row of the chunk 8 ahead (tools/stress_k3b.py); a parity check of a single launch misses that most of the time."""
+    import torch
+    lib, p, ck = be.lib, be.ptr, be.check
+    B, C0, C1, Cout, H, W, m1, m2 = FULL_SHAPES[2]
+    Cin = C0 + C1
+    g = torch.Generator(device=be.dev).manual_seed(5)
+    rn = lambda *s: torch.randn(*s, device=be.dev, generator=g)
+    Z, x0, x1 = rn(B, H, 2 * m2, Cout), rn(B, C0, H, W), rn(B, C1, H, W)
+    wc, bias, res = rn(Cout, Cin) / Cin ** 0.5, rn(Cout), rn(B, Cout, H, W)
+    tab = be.tables(H, W, m1, m2)
+    pack = be.empty((lib.pdes_gemm_tc_pack_floats(Cin, Cout),))
+    ck(lib.pdes_gemm_tc_pack_t(p(wc), Cin, Cin, Cout, p(pack), be.stream))
+    flush = torch.zeros(48 * 1024 * 1024, device=be.dev)
+
+    def run():
+        out = be.empty((B, Cout, H, W))
+        ck(lib.pdes_inv_w_gemm_tc(p(Z), p(pack), p(x0), C0, p(x1), C1, p(bias), p(res), p(tab), 0, p(out), None,
+                                  B, Cout, H, W, m1, m2, 1, be.stream))
+        return out
+
+    first = run()
+    for i in range(150):
+        if i % 2:
+            flush.add_(1.0)                       # cold and warm L2: the race window depended on the copy latency
+        assert torch.equal(run().view(torch.int32), first.view(torch.int32)), f"launch {i} differs from launch 0"
