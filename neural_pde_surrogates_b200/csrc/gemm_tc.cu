@@ -364,7 +364,7 @@ constexpr int kV3TaMaxN = 208;
 template <bool kTA>
 __global__ void __launch_bounds__(kK3Threads, 1)
 k_inv_w_gemm_tc_v3(TcParams p, int B, int ntiles_per_img, const __grid_constant__ CUtensorMap tmap_x0, int ntmap_chunks,
-                   int NST, int NRAW) {
+                   int NST, int NRAW, int nfull, int tail_shift) {
   PDES_DYN_SMEM(unsigned char, smem_raw);
   unsigned char* base = ptx::align_smem_1024(smem_raw);
   const int npad = p.npad;
@@ -412,7 +412,17 @@ k_inv_w_gemm_tc_v3(TcParams p, int B, int ntiles_per_img, const __grid_constant_
   ptx::tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
 
-  // per-tile geometry (identical in every role)
+  // Work items (identical in every role).  Items [0, nfull) are whole 128-pixel x npad-column tiles, nfull a multiple of
+  // the grid.  The ntiles - nfull tiles of the last, partly filled round are cut into 2^tail_shift column ranges each so
+  // that (almost) every CTA gets a piece: at B = 16 the 768 tiles ran as 6 rounds on 148 CTAs for 5.19 rounds of work.
+  const int nitems = nfull + ((ntiles - nfull) << tail_shift);
+  auto item_geom = [&](int i, int& t, int& n0, int& ncols) {
+    if (i < nfull) { t = i; n0 = 0; ncols = npad; return; }
+    const int j = i - nfull;
+    t = nfull + (j >> tail_shift);
+    ncols = npad >> tail_shift;
+    n0 = (j & ((1 << tail_shift) - 1)) * ncols;
+  };
   auto tile_geom = [&](int t, int& b, int& p0, int& h0, int& kspec, int& nsp) {
     b = t / ntiles_per_img;
     p0 = (t - b * ntiles_per_img) * kTcM;
@@ -456,14 +466,16 @@ k_inv_w_gemm_tc_v3(TcParams p, int B, int ntiles_per_img, const __grid_constant_
         for (; j < J; ++j) dst[j * kTcM] = __ldg(tcol + (size_t)j * W);
       }
     };
-    if (p.Z != nullptr && uniform_geom && (int)blockIdx.x < ntiles) {
-      int b, p0, h0, kspec, nsp;
-      tile_geom(blockIdx.x, b, p0, h0, kspec, nsp);
+    if (p.Z != nullptr && uniform_geom && (int)blockIdx.x < nitems) {
+      int b, p0, h0, kspec, nsp, t0, n0, ncols;
+      item_geom(blockIdx.x, t0, n0, ncols);
+      tile_geom(t0, b, p0, h0, kspec, nsp);
       if (grp == 0) build_tsp(p0, h0, kspec, nsp);                // column tid is read by thread tid of BOTH groups
       cvt_sync();
     }
-    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
-      int b, p0, h0, kspec, nsp;
+    for (int i = blockIdx.x; i < nitems; i += gridDim.x) {
+      int b, p0, h0, kspec, nsp, t, n0, ncols;
+      item_geom(i, t, n0, ncols);
       tile_geom(t, b, p0, h0, kspec, nsp);
       const int pp = p0 + tid;
       const bool pvalid = pp < HW;
@@ -501,7 +513,7 @@ k_inv_w_gemm_tc_v3(TcParams p, int B, int ntiles_per_img, const __grid_constant_
           const float* rw = raw + (size_t)r * slot_f;                     // Z rows: dense [16][N]
           unsigned char* sb = sB + s * b_stage;
           // one (n, 4 consecutive k) item = one 16-byte row of a core matrix: conflict-free LDS and STS.128
-          for (int n = tid; n < npad; n += 128) {
+          for (int n = n0 + tid; n < n0 + ncols; n += 128) {               // only the item's column range is multiplied
 #pragma unroll
             for (int kq = 0; kq < kTcBK / 4; ++kq) {
               float z[4];
@@ -572,16 +584,18 @@ k_inv_w_gemm_tc_v3(TcParams p, int B, int ntiles_per_img, const __grid_constant_
   } else if (warp == kK3MmaWarp) {
     {
       // ================================================================ MMA issue (warp-converged, one elected lane issues)
-      const uint32_t idesc = ptx::idesc_tf32(kTcM, npad);
       const uint32_t lbo_a = (kTcM / 8) * 128, lbo_b = (uint32_t)(npad / 8) * 128, sbo = 128;
       const uint64_t a_hi0 = ptx::smem_desc_noswizzle(ptx::smem_u32(sA), lbo_a, sbo);
       const uint64_t a_lo0 = ptx::smem_desc_noswizzle(ptx::smem_u32(sA) + a_blk, lbo_a, sbo);
       const uint64_t b_hi0 = ptx::smem_desc_noswizzle(ptx::smem_u32(sB), lbo_b, sbo);
       const uint64_t b_lo0 = ptx::smem_desc_noswizzle(ptx::smem_u32(sB) + b_blk, lbo_b, sbo);
       uint32_t g = 0, it = 0, s = 0, sph = 0;
-      for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
-        int b, p0, h0, kspec, nsp;
+      for (int i = blockIdx.x; i < nitems; i += gridDim.x, ++it) {
+        int b, p0, h0, kspec, nsp, t, n0, ncols;
+        item_geom(i, t, n0, ncols);
         tile_geom(t, b, p0, h0, kspec, nsp);
+        const uint32_t idesc = ptx::idesc_tf32(kTcM, ncols);
+        const uint64_t bcol = (uint64_t)(((uint32_t)(n0 >> 3) * 128u) >> 4);  // the item's first 8-column block of the B stage
         const uint32_t a = it & 1;
         TRACE(3 * 512 + 256 + it * 2 + 0);
         if (it >= 2) ptx::mbar_wait(&bars.acc_empty[a], ((it / 2) - 1) & 1);
@@ -599,7 +613,7 @@ k_inv_w_gemm_tc_v3(TcParams p, int B, int ntiles_per_img, const __grid_constant_
           TRACE2(g * 10 + 2);
           ptx::tc_fence_after();
           // only the 14-bit start-address field of a descriptor changes between stages / K steps
-          const uint64_t da = (uint64_t)((s * a_stage) >> 4), db = (uint64_t)((s * b_stage) >> 4);
+          const uint64_t da = (uint64_t)((s * a_stage) >> 4), db = (uint64_t)((s * b_stage) >> 4) + bcol;
 #pragma unroll
           for (int ks = 0; ks < kTcBK / 8; ++ks) {
             const uint64_t ka = da + (uint64_t)((ks * 2 * lbo_a) >> 4), kb = db + (uint64_t)((ks * 2 * lbo_b) >> 4);
@@ -639,8 +653,9 @@ k_inv_w_gemm_tc_v3(TcParams p, int B, int ntiles_per_img, const __grid_constant_
       // The activations come from HBM (not L2): at ~1.2 us loaded latency a 3-slot ring (24 KB in flight per SM) paced
       // the whole kernel at ~1250 cycles per chunk; the ring is now as deep as shared memory allows (up to 8 slots).
       uint32_t g = 0, r = 0, rph = 1;
-      for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        int b, p0, h0, kspec, nsp;
+      for (int i = blockIdx.x; i < nitems; i += gridDim.x) {
+        int b, p0, h0, kspec, nsp, t, n0, ncols;
+        item_geom(i, t, n0, ncols);
         tile_geom(t, b, p0, h0, kspec, nsp);
         const int npx = (HW - p0 < kTcM) ? (HW - p0) : kTcM;
         // (a TMA L2 prefetch of this tile's residual [N][128 px], issued here, was measured on B200: 72.3 -> 77.2 us, like
@@ -685,8 +700,9 @@ k_inv_w_gemm_tc_v3(TcParams p, int B, int ntiles_per_img, const __grid_constant_
     {
       // ================================================================ B ring issue (warp-converged) (packed weight chunks)
       uint32_t g = 0, s = 0, sph = 1;
-      for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        int b, p0, h0, kspec, nsp;
+      for (int i = blockIdx.x; i < nitems; i += gridDim.x) {
+        int b, p0, h0, kspec, nsp, t, n0, ncols;
+        item_geom(i, t, n0, ncols);
         tile_geom(t, b, p0, h0, kspec, nsp);
         for (int c = 0; c < nsp + nx; ++c, ++g) {
           if (g >= (uint32_t)NST) ptx::mbar_wait(&bars.empty[s], sph);
@@ -708,13 +724,14 @@ k_inv_w_gemm_tc_v3(TcParams p, int B, int ntiles_per_img, const __grid_constant_
     // (a fully unrolled 32-column body was > 30 KB of SASS and ran out of the instruction cache: 270 cycles/output).
     const int quad = warp & 3, part = (warp - 8) >> 2;
     const int N = p.N;
-    const int nq = (npad + 7) / 8;                                   // 8-column groups
-    const int per = (nq + kK3EpiParts - 1) / kK3EpiParts;
-    const int qbeg = (part * per < nq) ? part * per : nq, qend = (qbeg + per < nq) ? qbeg + per : nq;
     uint32_t it = 0;
-    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
-      int b, p0, h0, kspec, nsp;
+    for (int i = blockIdx.x; i < nitems; i += gridDim.x, ++it) {
+      int b, p0, h0, kspec, nsp, t, nbase, ncols;
+      item_geom(i, t, nbase, ncols);
       tile_geom(t, b, p0, h0, kspec, nsp);
+      const int nq = ncols / 8;                                      // 8-column groups of this item (TMEM columns [0, ncols))
+      const int per = (nq + kK3EpiParts - 1) / kK3EpiParts;
+      const int qbeg = (part * per < nq) ? part * per : nq, qend = (qbeg + per < nq) ? qbeg + per : nq;
       const int pp = p0 + quad * 32 + lane;
       const bool pvalid = pp < HW;
       // 32-bit element offsets (the host guarantees B * out_bs < 2^32): one IMAD.WIDE per access instead of a 64-bit
@@ -729,7 +746,7 @@ k_inv_w_gemm_tc_v3(TcParams p, int B, int ntiles_per_img, const __grid_constant_
       float cur[8], nxt[8], nx2[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        const int n = qbeg * 8 + e;
+        const int n = nbase + qbeg * 8 + e;
         cur[e] = (has_res && qbeg < qend && n < N) ? __ldg(p.res + (obase + (uint32_t)n * uHW)) : 0.0f;
         nxt[e] = (has_res && qbeg + 1 < qend && n + 8 < N) ? __ldg(p.res + (obase + (uint32_t)(n + 8) * uHW)) : 0.0f;
       }
@@ -748,14 +765,14 @@ k_inv_w_gemm_tc_v3(TcParams p, int B, int ntiles_per_img, const __grid_constant_
       const uint32_t tbase = tmem_base + a * 256 + ((uint32_t)(quad * 32) << 16);
 #pragma unroll 1
       for (int qi = qbeg; qi < qend; ++qi) {
-        const int n0 = qi * 8;
+        const int c0 = qi * 8, n0 = nbase + c0;                      // TMEM column and output channel of the group
 #pragma unroll
         for (int e = 0; e < 8; ++e) {                                // prefetch the residual of the group after the next
           const int n = n0 + 16 + e;
           nx2[e] = (has_res && qi + 2 < qend && n < N) ? __ldg(p.res + (obase + (uint32_t)n * uHW)) : 0.0f;
         }
         uint32_t r[8];
-        ptx::tmem_ld8(tbase + (uint32_t)n0, r);
+        ptx::tmem_ld8(tbase + (uint32_t)c0, r);
         ptx::tmem_ld_wait();
         if (qi + 1 == qend) {                                        // accumulator fully read: hand it back to the MMA warp
           ptx::tc_fence_before();
@@ -1573,8 +1590,16 @@ int inv_w_gemm_tc_impl(const float* Z, const float* wpack, const float* x0, int 
 #endif
     auto k3 = v3_ta ? k_inv_w_gemm_tc_v3<true> : k_inv_w_gemm_tc_v3<false>;
     PDES_SET_SMEM(k3, smem3);
-    PDES_LAUNCH(k3, dim3((unsigned)(ntiles < g_num_sms ? ntiles : g_num_sms)), dim3(kK3Threads), smem3, stream, p, B,
-                tiles_per_img, tmap, ntmap_chunks, v3_nst, v3_nraw);
+    // the last, partly filled round of tiles is cut into 2 or 4 column ranges when that gives every tile piece its own CTA
+    const int grid3 = ntiles < g_num_sms ? ntiles : g_num_sms;
+    const int nfull = (ntiles / grid3) * grid3, ntail = ntiles - nfull;
+    int tail_shift = 0;
+    if (ntail > 0 && nfull > 0 && getenv("PDES_K3B_NO_TAIL_SPLIT") == nullptr) {
+      if (ntail * 4 <= grid3 && p.npad % 64 == 0) tail_shift = 2;
+      else if (ntail * 2 <= grid3 && p.npad % 32 == 0) tail_shift = 1;
+    }
+    PDES_LAUNCH(k3, dim3((unsigned)grid3), dim3(kK3Threads), smem3, stream, p, B, tiles_per_img, tmap, ntmap_chunks, v3_nst,
+                v3_nraw, nfull, tail_shift);
 #ifdef PDES_TC_TRACE
 #undef v3_nst
 #undef v3_nraw
