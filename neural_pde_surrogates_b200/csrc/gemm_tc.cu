@@ -653,6 +653,9 @@ k_inv_w_gemm_tc_v3(TcParams p, int B, int ntiles_per_img, const __grid_constant_
       // The activations come from HBM (not L2): at ~1.2 us loaded latency a 3-slot ring (24 KB in flight per SM) paced
       // the whole kernel at ~1250 cycles per chunk; the ring is now as deep as shared memory allows (up to 8 slots).
       uint32_t g = 0, r = 0, rph = 1;
+      // last read of the activations in the forward chain (K1 kept them in L2 with evict-last): evict-first frees the
+      // lines for the part of the input that has not been read yet
+      const uint64_t pol_last_use = ptx::l2_policy_evict_first();
       for (int i = blockIdx.x; i < nitems; i += gridDim.x) {
         int b, p0, h0, kspec, nsp, t, n0, ncols;
         item_geom(i, t, n0, ncols);
@@ -680,7 +683,7 @@ k_inv_w_gemm_tc_v3(TcParams p, int B, int ntiles_per_img, const __grid_constant_
                 ptx::mbar_arrive_ws(&bars.raw_full[r]);
               } else {
               ptx::mbar_arrive_expect_tx_ws(&bars.raw_full[r], (uint32_t)kTcBK * kTcM * 4);
-              ptx::tma_load_2d_ws(dst, &tmap_x0, p0, b * p.C0 + cx * kTcBK, &bars.raw_full[r]);
+              ptx::tma_load_2d_ws_hint(dst, &tmap_x0, p0, b * p.C0 + cx * kTcBK, &bars.raw_full[r], pol_last_use);
               }
             } else {
               ptx::mbar_arrive_expect_tx_ws(&bars.raw_full[r], (uint32_t)nk * npx * 4);
@@ -747,8 +750,8 @@ k_inv_w_gemm_tc_v3(TcParams p, int B, int ntiles_per_img, const __grid_constant_
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const int n = nbase + qbeg * 8 + e;
-        cur[e] = (has_res && qbeg < qend && n < N) ? __ldg(p.res + (obase + (uint32_t)n * uHW)) : 0.0f;
-        nxt[e] = (has_res && qbeg + 1 < qend && n + 8 < N) ? __ldg(p.res + (obase + (uint32_t)(n + 8) * uHW)) : 0.0f;
+        cur[e] = (has_res && qbeg < qend && n < N) ? __ldcs(p.res + (obase + (uint32_t)n * uHW)) : 0.0f;
+        nxt[e] = (has_res && qbeg + 1 < qend && n + 8 < N) ? __ldcs(p.res + (obase + (uint32_t)(n + 8) * uHW)) : 0.0f;
       }
       if (tid == 256) TRACE(3 * 512 + it * 4 + 0);
       ptx::mbar_wait(&bars.acc_full[a], (it / 2) & 1);
@@ -769,7 +772,7 @@ k_inv_w_gemm_tc_v3(TcParams p, int B, int ntiles_per_img, const __grid_constant_
 #pragma unroll
         for (int e = 0; e < 8; ++e) {                                // prefetch the residual of the group after the next
           const int n = n0 + 16 + e;
-          nx2[e] = (has_res && qi + 2 < qend && n < N) ? __ldg(p.res + (obase + (uint32_t)n * uHW)) : 0.0f;
+          nx2[e] = (has_res && qi + 2 < qend && n < N) ? __ldcs(p.res + (obase + (uint32_t)n * uHW)) : 0.0f;
         }
         uint32_t r[8];
         ptx::tmem_ld8(tbase + (uint32_t)c0, r);
@@ -799,18 +802,18 @@ k_inv_w_gemm_tc_v3(TcParams p, int B, int ntiles_per_img, const __grid_constant_
               float2 v = make_float2(cur[e] + bz[e], cur[e + 1] + bz[e + 1]);
               ffma2(v, make_float2(__uint_as_float(r[e]), __uint_as_float(r[e + 1])), make_float2(1.0f, 1.0f));
               const uint32_t oa = o0 + (uint32_t)e * uHW, ob = oa + uHW;
-              if (has_pre) { pq[oa] = v.x; pq[ob] = v.y; }
+              if (has_pre) { __stcs(pq + oa, v.x); __stcs(pq + ob, v.y); }
               if (do_gelu) v = gelu_fast2_f(v);
-              po[oa] = v.x;
-              po[ob] = v.y;
+              __stcs(po + oa, v.x);                                  // streaming: the output must not evict the input
+              __stcs(po + ob, v.y);
             }
           } else {
             for (int e = 0; e < 8 && n0 + e < N; ++e) {
               float v = __uint_as_float(r[e]) + cur[e];
               v += bias_s[n0 + e];
-              if (has_pre) pq[o0 + (uint32_t)e * uHW] = v;
+              if (has_pre) __stcs(pq + (o0 + (uint32_t)e * uHW), v);
               if (do_gelu) v = gelu_fast_f(v);
-              po[o0 + (uint32_t)e * uHW] = v;
+              __stcs(po + (o0 + (uint32_t)e * uHW), v);
             }
           }
         }

@@ -68,6 +68,25 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                : "memory");
 }
 
+// ---- L2 residency hints.  The block reads its input h twice (K1, then K3b); 75 MB fits the 126 MB L2 if the streams in
+// between (K2's 59 MB of weights, K3b's residual and output) are marked evict-first and h itself evict-last.
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void bulk_g2s_hint(void* dst, const void* src, uint32_t bytes, void* bar, uint64_t pol) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+               : "memory");
+}
+
 // 2-D tiled TMA load (SASS UTMALDG): box described by a CUtensorMap, coordinates {c0 (inner), c1}
 __device__ __forceinline__ void tma_load_2d(void* dst, const void* tmap, int c0, int c1, void* bar) {
   asm volatile(
@@ -221,6 +240,15 @@ __device__ __forceinline__ void tma_load_3d_ws(void* dst, const void* tmap, int 
       "@e cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n\t}" ::"r"(
           smem_u32(dst)),
       "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_ws_hint(void* dst, const void* tmap, int c0, int c1, void* bar, uint64_t pol) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], "
+      "%5;\n\t}" ::"r"(smem_u32(dst)),
+      "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "l"(pol)
       : "memory");
 }
 // L2 prefetch of a 2-D tensor-map box (no shared memory, no completion tracking): one elected lane issues

@@ -214,7 +214,8 @@ k_dft_fwd_fast(const float* __restrict__ x0, int C0, const float* __restrict__ x
     // the stage-2 twiddle table arrives with the image: a second bulk copy on the same mbarrier (ncu: the per-thread
     // __ldg fill of this table was 21 % of the kernel's stall samples, a dependent global-load phase in every CTA)
     ptx::mbar_arrive_expect_tx(&mbar, H * W * 4 + M2 * (W + 1) * 8);
-    ptx::bulk_g2s(img, src, H * W * 4, &mbar);
+    // the image is read again by K3b two kernels later: keep it in L2 (evict-last) across K2's weight stream
+    ptx::bulk_g2s_hint(img, src, H * W * 4, &mbar, ptx::l2_policy_evict_last());
     ptx::bulk_g2s(&tw2[0][0], tw2_g, M2 * (W + 1) * 8, &mbar);
   }
   (void)twa_g; (void)nc4;

@@ -108,10 +108,10 @@ k_mix_tc_pack(const float2* __restrict__ w1, const float2* __restrict__ w2, floa
 // Each thread keeps HP = 8 row pairs in registers (32 accumulators), so one spectrum load and four 128-bit twiddle loads
 // feed 32 FMAs.
 constexpr int kIh2HP = 8;                                // row pairs per thread
-constexpr int kIh2MaxWarps = 16;
+constexpr int kIh2Warps = 3;
 // (A persistent, cp.async double-buffered variant of this kernel was measured on B200 and was not faster -- 23.0 vs
 // 20.5 us in the cold-cache ncu pass -- so the simple one-CTA-per-item form stays.)
-__global__ void __launch_bounds__(32 * kIh2MaxWarps)
+__global__ void __launch_bounds__(32 * kIh2Warps)
 k_inv_h2(const float2* __restrict__ O2, int B, int C, int H, int m1, int m2,
          const float2* __restrict__ twp_g, float* __restrict__ Z) {
   PDES_DYN_SMEM(float2, sm2);
@@ -398,6 +398,7 @@ k_mix_tc(MtParams p, const __grid_constant__ CUtensorMap tmap_w, const __grid_co
       int m = item0 / p.ntile, t = item0 - m * p.ntile, kc = kc_first + q;
       while (kc >= p.nck) { kc -= p.nck; if (++t == p.ntile) { t = 0; ++m; } }
       int s = q;
+      const uint64_t pol_stream = ptx::l2_policy_evict_first();
       uint32_t eph = 1;                                                      // parity of empty[s] (first pass: no wait)
       for (int g = q; g < nloc; g += 4) {
         if (q == 0 && lane == 0) MT_TRACE(0, g, 0);
@@ -408,7 +409,9 @@ k_mix_tc(MtParams p, const __grid_constant__ CUtensorMap tmap_w, const __grid_co
           ptx::mbar_arrive_ws(&bars.raw_full[s]);
         } else {
           ptx::mbar_arrive_expect_tx_ws(&bars.raw_full[s], wbytes + xbytes);
-          ptx::tma_load_2d_ws(st, &tmap_w, 0, (c_beg + g) * p.to, &bars.raw_full[s]);       // chunk c = one contiguous block
+          // the packed weights are read exactly once per forward (59 MB): evict-first, so that they do not push the
+          // block input out of L2 between K1 and K3b
+          ptx::tma_load_2d_ws_hint(st, &tmap_w, 0, (c_beg + g) * p.to, &bars.raw_full[s], pol_stream);   // one contiguous block
           ptx::tma_load_2d_ws(st + x_off, &tmap_x, kc * 2 * kMtBK, m * p.B, &bars.raw_full[s]);
         }
         if (q == 0 && lane == 0) MT_TRACE(0, g, 2);
@@ -648,7 +651,10 @@ int pdes_inv_h_modes(const float* O2, int B, int C, int H, int m1, int m2, const
                "pdes_inv_h_modes: needs %zu B of shared memory", smem);
   PDES_REQUIRE(B <= 65535 && m2 <= 65535, PDES_ERR_UNSUPPORTED, "pdes_inv_h_modes: grid too large");
   int nwarp = ceil_div(npair, kIh2HP);
-  if (nwarp > kIh2MaxWarps) nwarp = kIh2MaxWarps;
+  // Three warps per CTA (each takes every third block of 8 row pairs): at the shipped shape the 960 CTAs are then all
+  // resident at once (7 per SM by registers).  With one warp per block (7 warps) only 592 fit and the grid ran as 1.6
+  // waves: 16.6 -> 14.5 us back to back, 4 us off the chain in situ (tools/sweep_k3a.py).
+  if (nwarp > kIh2Warps) nwarp = kIh2Warps;
   auto kfn = k_inv_h2;
   if (smem > 48 * 1024) PDES_SET_SMEM(kfn, smem);
   PDES_MAX_CARVEOUT(kfn);

@@ -184,3 +184,51 @@ def test_tc_inverse_gemm_run_to_run_bitwise(be):
         if i % 2:
             flush.add_(1.0)                       # cold and warm L2: the race window depended on the copy latency
         assert torch.equal(run().view(torch.int32), first.view(torch.int32)), f"launch {i} differs from launch 0"
+
+
+@pytest.mark.parametrize("B", [4, 16])
+def test_block_forward_backward_run_to_run_bitwise(be, B):
+    """No kernel of the block uses atomics, so every output of pdes_block_forward / pdes_block_backward must repeat bit for
+    bit.  100 launches with alternating cold / warm L2 at the shipped shape: the check that exposes ring races (a
+    consumer releasing a stage before its loads landed, a producer overtaking a reader), which corrupt one tile in
+    thousands and slip through a single parity comparison."""
+    import torch
+    lib, p, ck = be.lib, be.ptr, be.check
+    _, C0, C1, Cout, H, W, m1, m2 = FULL_SHAPES[2]
+    Cin, st = C0 + C1, be.stream
+    g = torch.Generator(device=be.dev).manual_seed(11)
+    rn = lambda *s: torch.randn(*s, device=be.dev, generator=g)
+    h, vb, res, gout = rn(B, C0, H, W), rn(B, C1, H, W), rn(B, Cout, H, W), rn(B, Cout, H, W)
+    w1 = torch.view_as_complex(rn(Cin, Cout, m1, m2, 2).contiguous()) / Cin
+    w2 = torch.view_as_complex(rn(Cin, Cout, m1, m2, 2).contiguous()) / Cin
+    wc, bias = rn(Cout, Cin) / Cin ** 0.5, rn(Cout)
+    tab = be.tables(H, W, m1, m2)
+    wsp = be.empty((lib.pdes_mix_tc_pack_floats(Cin, Cout, m1, m2),))
+    ck(lib.pdes_mix_tc_pack(p(w1), p(w2), p(wsp), Cin, Cout, H, m1, m2, st))
+    pack_f = be.empty((lib.pdes_gemm_tc_pack_floats(Cin, Cout),))
+    ck(lib.pdes_gemm_tc_pack_t(p(wc), Cin, Cin, Cout, p(pack_f), st))
+    ws = be.empty((lib.pdes_block_fwd_workspace_floats(B, Cin, Cout, H, W, m1, m2),))
+    wsb = be.empty((lib.pdes_block_bwd_workspace_floats(B, C0, C1, Cout, H, W, m1, m2),))
+    flush = torch.zeros(48 * 1024 * 1024, device=be.dev)
+
+    def run():
+        X = be.empty((B, Cin, 2 * m1, m2), complex_=True)
+        out, pre = be.empty((B, Cout, H, W)), be.empty((B, Cout, H, W))
+        ck(lib.pdes_block_forward(p(h), C0, p(vb), C1, p(w1), p(w2), p(wsp), p(wc), p(pack_f), p(bias), p(res), p(tab), p(X),
+                                  p(ws), p(out), p(pre), B, Cout, H, W, m1, m2, 1, st))
+        gpre, dh = be.empty((B, Cout, H, W)), be.empty((B, C0, H, W))
+        gw1, gw2 = be.empty(tuple(w1.shape), complex_=True), be.empty(tuple(w2.shape), complex_=True)
+        dwc, dbias = be.empty((Cout, Cin)), be.empty((Cout,))
+        ck(lib.pdes_block_backward(p(gout), p(pre), p(h), C0, p(vb), C1, p(X), p(w1), p(w2), p(wc), None, p(tab), p(wsb),
+                                   p(gpre), p(dh), p(gw1), p(gw2), p(dwc), p(dbias), B, Cout, H, W, m1, m2, 1, st))
+        return dict(X=torch.view_as_real(X), out=out, pre=pre, gpre=gpre, dh=dh, gw1=torch.view_as_real(gw1),
+                    gw2=torch.view_as_real(gw2), dwc=dwc, dbias=dbias)
+
+    first = run()
+    assert all(torch.isfinite(v).all() for v in first.values())
+    for i in range(100):
+        if i % 2:
+            flush.add_(1.0)
+        now = run()
+        bad = [k for k in first if not torch.equal(now[k].view(torch.int32), first[k].view(torch.int32))]
+        assert not bad, f"launch {i}: {bad} differ from launch 0"
