@@ -48,6 +48,9 @@ int check_launch(const char* what);
 
 // driver entry point cuTensorMapEncodeTiled fetched through the runtime (no libcuda link); nullptr if unavailable
 void* tensor_map_encoder();
+// K1 on tcgen05 (spectral_dft_tc.cu): -1 = shape / build outside that kernel, otherwise a PDES_* code
+int dft_fwd_tc_try(const float* x0, int C0, const float* x1, int C1, int B, int H, int W, int m1, int m2, const float* tables,
+                   int herm_scale, float* X, float* X2, int CinP, void* stream);
 // TMA-fed K2 (spectral_mix_tma.cu): reduction splits it wants (0 = unsupported shape) and the launcher
 // (PDES_ERR_UNSUPPORTED = caller falls back to the generic kernels)
 int mix_tma_splits(int B, int Cred, int Cn, int m1, int m2);

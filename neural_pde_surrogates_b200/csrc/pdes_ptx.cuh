@@ -251,6 +251,15 @@ __device__ __forceinline__ void tma_load_2d_ws_hint(void* dst, const void* tmap,
       "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "l"(pol)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_3d_ws_hint(void* dst, const void* tmap, int c0, int c1, int c2, void* bar, uint64_t pol) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4}], "
+      "[%5], %6;\n\t}" ::"r"(smem_u32(dst)),
+      "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)), "l"(pol)
+      : "memory");
+}
 // L2 prefetch of a 2-D tensor-map box (no shared memory, no completion tracking): one elected lane issues
 __device__ __forceinline__ void tma_prefetch_2d_ws(const void* tmap, int c0, int c1) {
   asm volatile(
@@ -273,6 +282,24 @@ __device__ __forceinline__ uint64_t smem_desc_noswizzle(uint32_t saddr, uint32_t
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;     // descriptor version = 1 (Blackwell)
   return d;                   // base_offset = 0, lbo_mode = 0, layout_type = SWIZZLE_NONE (0)
+}
+// shared-memory matrix descriptor of an MN-major tf32 operand: rows of 32 consecutive M (or N) elements (128 bytes) per K
+// index, swizzle mode SWIZZLE_128B_BASE32B (layout type 1): the four 32-byte chunks of a row are XOR-ed with (row % 4) --
+// what a TMA box {32 floats, rows} with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B writes.  (Measured on B200: with the ordinary
+// SWIZZLE_128B layout type an MN-major tf32 operand multiplies as zeros.)  lbo = byte distance between consecutive
+// 32-element blocks along M/N, sbo = byte distance between groups of 4 K rows (512 when the rows are contiguous).
+__device__ __forceinline__ uint64_t smem_desc_mn_sw128b32(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;
+  return d;
+}
+// instruction descriptor with A read MN-major (bit 15): D = f32, A = B = tf32, B K-major
+__device__ __forceinline__ uint32_t idesc_tf32_a_mn(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 // instruction descriptor: D = f32, A = B = tf32, both K-major, dense, M x N
 __device__ __forceinline__ uint32_t idesc_tf32(int M, int N) {

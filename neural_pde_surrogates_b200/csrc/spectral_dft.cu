@@ -287,6 +287,10 @@ int dft_fwd_impl(const float* x0, int C0, const float* x1, int C1, int B, int H,
   PDES_REQUIRE(m1 > 0 && m2 > 0 && m1 <= H && m2 <= W / 2 + 1, PDES_ERR_ARG,
                "modes (%d,%d) exceed the grid (%d,%d): need m1 <= H and m2 <= W/2+1", m1, m2, H, W);
   const TableLayout t = table_layout(H, W, m1, m2);
+  {
+    const int rc = dft_fwd_tc_try(x0, C0, x1, C1, B, H, W, m1, m2, tables, herm_scale, X, X2f, CinP, stream);
+    if (rc >= 0) return rc;
+  }
   if (H == 96 && W == 64 && m1 == 10 && m2 == 10 && aligned16(x0) && (x1 == nullptr || aligned16(x1)) && aligned16(tables)) {
     auto kfast = k_dft_fwd_fast<96, 64, 10, 10>;
     PDES_MAX_CARVEOUT(kfast);

@@ -232,3 +232,14 @@ def test_block_forward_backward_run_to_run_bitwise(be, B):
         now = run()
         bad = [k for k in first if not torch.equal(now[k].view(torch.int32), first[k].view(torch.int32))]
         assert not bad, f"launch {i}: {bad} differ from launch 0"
+
+
+@pytest.mark.parametrize("herm", [0, 1])
+def test_dft_fwd_tensor_core_opt_in(be, herm, monkeypatch):
+    """The opt-in tcgen05 K1 (both DFT stages as 3xTF32 GEMMs with MN-major operands, csrc/spectral_dft_tc.cu) against the
+    float64 oracle at the shipped grid, odd image count and two input tensors included."""
+    monkeypatch.setenv("PDES_K1_TC", "1")
+    for shape in [(1, 3, 1, 4, 96, 64, 10, 10), (2, 4, 1, 8, 96, 64, 10, 10), (3, 5, 0, 4, 32, 64, 4, 7), (4, 192, 1, 192, 96, 64, 10, 10)]:
+        kc.check_dft_fwd(be, shape, herm)
+    monkeypatch.delenv("PDES_K1_TC")
+    kc.check_dft_fwd(be, (1, 3, 1, 4, 96, 64, 10, 10), herm)

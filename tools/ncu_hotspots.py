@@ -10,7 +10,8 @@ n = int(sys.argv[3]) if len(sys.argv) > 3 else 16
 txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", f"regex:{pat}"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(txt)))
 start = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
-hdr, data = rows[start], [r for r in rows[start + 1:] if len(r) == len(rows[start])]
+hdr = rows[start]
+data = [r for r in rows[start + 1:] if len(r) == len(hdr) and r[0] != "Address"]     # (several launches: the header repeats)
 ci = {h: i for i, h in enumerate(hdr)}
 stalls = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
 tot = sum(int(r[ci["# Samples"]] or 0) for r in data)
