@@ -380,7 +380,6 @@ k_inv_w_gemm_tc_v3(TcParams p, int B, int ntiles_per_img, const __grid_constant_
   __shared__ __align__(8) V3RingBars bars;
   __shared__ uint32_t tmem_slot;
   __shared__ __align__(16) float bias_s[kTcMaxN];      // the epilogue stalled on per-group __ldg(bias) (ncu: 18 % of all samples)
-  for (int i = threadIdx.x; i < kTcMaxN; i += blockDim.x) bias_s[i] = (p.bias != nullptr && i < p.N) ? __ldg(p.bias + i) : 0.0f;
 
   // warp index as a warp-uniform value: the single-issuer roles below run with the whole warp converged and one elected
   // lane issuing (ptx::*_ws), which keeps their operands in uniform registers (no waterfall loop per tcgen05 / TMA issue)
@@ -407,6 +406,10 @@ k_inv_w_gemm_tc_v3(TcParams p, int B, int ntiles_per_img, const __grid_constant_
     ptx::tmem_alloc(&tmem_slot, 512);
     ptx::tmem_relinquish();
   }
+  // Launched as a programmatic dependent of the previous kernel in the stream: everything above overlaps its tail; no
+  // global memory is read before this point.
+  PDES_GRID_DEP_WAIT();
+  for (int i = threadIdx.x; i < kTcMaxN; i += blockDim.x) bias_s[i] = (p.bias != nullptr && i < p.N) ? __ldg(p.bias + i) : 0.0f;
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -1601,8 +1604,8 @@ int inv_w_gemm_tc_impl(const float* Z, const float* wpack, const float* x0, int 
       if (ntail * 4 <= grid3 && p.npad % 64 == 0) tail_shift = 2;
       else if (ntail * 2 <= grid3 && p.npad % 32 == 0) tail_shift = 1;
     }
-    PDES_LAUNCH(k3, dim3((unsigned)grid3), dim3(kK3Threads), smem3, stream, p, B, tiles_per_img, tmap, ntmap_chunks, v3_nst,
-                v3_nraw, nfull, tail_shift);
+    PDES_LAUNCH_PDL(k3, dim3((unsigned)grid3), dim3(kK3Threads), smem3, stream, p, B, tiles_per_img, tmap, ntmap_chunks,
+                    v3_nst, v3_nraw, nfull, tail_shift);
 #ifdef PDES_TC_TRACE
 #undef v3_nst
 #undef v3_nraw

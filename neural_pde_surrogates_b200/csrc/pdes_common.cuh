@@ -4,6 +4,7 @@
 #include "pdes_emu.h"
 #ifndef PDES_CPU_EMU
 #include <cuda_runtime.h>
+#include <cstdlib>
 #define PDES_DYN_SMEM(T, name)                                      \
   extern __shared__ __align__(16) unsigned char _pdes_dyn_smem[];   \
   T* name = reinterpret_cast<T*>(_pdes_dyn_smem)
@@ -11,6 +12,31 @@
   kernel<<<(grid), (block), (smem), (cudaStream_t)(stream)>>>(__VA_ARGS__)
 #define PDES_SET_SMEM(kernel, bytes) \
   cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))
+// Programmatic dependent launch: the kernel may be scheduled while its predecessor in the stream is still draining (after
+// every predecessor CTA executed griddepcontrol.launch_dependents or exited); it MUST execute PDES_GRID_DEP_WAIT() before
+// its first read of anything an earlier kernel wrote.  Hides the launch latency and the prologue (barrier init, TMEM
+// allocation, table loads) of the chain kernels behind the tail of the previous one.  PDES_NO_PDL=1 restores plain launches.
+namespace pdes {
+inline bool pdl_enabled() {
+  static const bool on = getenv("PDES_NO_PDL") == nullptr;
+  return on;
+}
+template <class K, class... A>
+inline void launch_pdl(K kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t stream, A... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+}  // namespace pdes
+#define PDES_LAUNCH_PDL(kernel, grid, block, smem, stream, ...) \
+  pdes::launch_pdl(kernel, (grid), (block), (smem), (cudaStream_t)(stream), __VA_ARGS__)
+#define PDES_GRID_DEP_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
+#define PDES_GRID_DEP_LAUNCH() asm volatile("griddepcontrol.launch_dependents;" ::: "memory")
 // Ask for the maximum shared-memory carve-out for a kernel of the block chain (once per call site).  The tcgen05 kernels
 // need ~220 KB of shared memory; a neighbour that runs with the default (small) carve-out forces the SMs to drain and
 // switch their L1 / shared-memory split at every kernel boundary of the chain.

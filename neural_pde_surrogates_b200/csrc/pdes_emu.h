@@ -92,5 +92,8 @@ static inline const char* cudaGetErrorString(cudaError_t) { return "emu"; }
   pdes_emu::launch((grid), (block), (smem), [&]() { kernel(__VA_ARGS__); })
 #define PDES_SET_SMEM(kernel, bytes) (0)
 #define PDES_MAX_CARVEOUT(kernel) do { } while (0)
+#define PDES_LAUNCH_PDL PDES_LAUNCH
+#define PDES_GRID_DEP_WAIT() do { } while (0)
+#define PDES_GRID_DEP_LAUNCH() do { } while (0)
 
 #endif  // PDES_CPU_EMU

@@ -238,6 +238,7 @@ k_dft_fwd_fast(const float* __restrict__ x0, int C0, const float* __restrict__ x
   }
   __syncthreads();
 
+  PDES_GRID_DEP_LAUNCH();                     // the next kernel of the chain (K2) may be scheduled behind this CTA's tail
   // ---- stage 2: row DFT of (P -+ iQ) to the M2 kept columns
   float* Xo = X + (size_t)im * (2 * M1 * M2) * 2;
   for (int item = tid; item < NK * M2; item += 2 * W) {

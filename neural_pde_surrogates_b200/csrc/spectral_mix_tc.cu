@@ -126,6 +126,7 @@ k_inv_h2(const float2* __restrict__ O2, int B, int C, int H, int m1, int m2,
   const int o = o0 + lane;
   // every global load of the block is issued before its one barrier
   for (int idx = tid; idx < NJ * npp; idx += nthr) tw[idx] = __ldg(twp_g + idx);     // host-built table, coalesced
+  PDES_GRID_DEP_WAIT();                                // O2 is written by the previous kernel of the chain (K2)
   const size_t pstride = (size_t)M2 * B * C;
   auto load_o = [&](int k, int oo) -> float2 {         // O[k][l] of channel oo = partial 0 + partial 1 (zero unless split)
     const size_t at = ((size_t)(k * m2 + l) * B + b) * C + oo;
@@ -146,6 +147,7 @@ k_inv_h2(const float2* __restrict__ O2, int B, int C, int H, int m1, int m2,
     Ds[idx] = dv;
   }
   __syncthreads();
+  PDES_GRID_DEP_LAUNCH();                              // K3b may be scheduled on an SM as soon as its K3a CTAs are gone
   for (int p0 = wq * kIh2HP; p0 < npair; p0 += nwarp * kIh2HP) {
     float pr[kIh2HP], pi[kIh2HP], qr[kIh2HP], qi[kIh2HP];
 #pragma unroll
@@ -400,6 +402,17 @@ k_mix_tc(MtParams p, const __grid_constant__ CUtensorMap tmap_w, const __grid_co
       int s = q;
       const uint64_t pol_stream = ptx::l2_policy_evict_first();
       uint32_t eph = 1;                                                      // parity of empty[s] (first pass: no wait)
+      // The weights do not depend on the previous kernel of the chain (K1 writes only the spectrum X2): the first pass over
+      // the ring streams its weight blocks BEFORE the grid-dependency wait (programmatic dependent launch), so the ~3 us
+      // until the first bytes arrive overlap K1's tail; the spectrum boxes of those stages follow after the wait.
+      if (!MT_DBG(2)) {
+        int sa = q;
+        for (int g = q; g < nloc && g < NST; g += 4, sa += 4) {
+          ptx::mbar_arrive_expect_tx_ws(&bars.raw_full[sa], wbytes + xbytes);
+          ptx::tma_load_2d_ws_hint(base + (uint32_t)sa * stage_bytes, &tmap_w, 0, (c_beg + g) * p.to, &bars.raw_full[sa], pol_stream);
+        }
+      }
+      PDES_GRID_DEP_WAIT();
       for (int g = q; g < nloc; g += 4) {
         if (q == 0 && lane == 0) MT_TRACE(0, g, 0);
         if (g >= NST) ptx::mbar_wait(&bars.empty[s], eph);
@@ -408,10 +421,12 @@ k_mix_tc(MtParams p, const __grid_constant__ CUtensorMap tmap_w, const __grid_co
         if (MT_DBG(2)) {
           ptx::mbar_arrive_ws(&bars.raw_full[s]);
         } else {
-          ptx::mbar_arrive_expect_tx_ws(&bars.raw_full[s], wbytes + xbytes);
-          // the packed weights are read exactly once per forward (59 MB): evict-first, so that they do not push the
-          // block input out of L2 between K1 and K3b
-          ptx::tma_load_2d_ws_hint(st, &tmap_w, 0, (c_beg + g) * p.to, &bars.raw_full[s], pol_stream);   // one contiguous block
+          if (g >= NST) {
+            ptx::mbar_arrive_expect_tx_ws(&bars.raw_full[s], wbytes + xbytes);
+            // the packed weights are read exactly once per forward (59 MB): evict-first, so that they do not push the
+            // block input out of L2 between K1 and K3b
+            ptx::tma_load_2d_ws_hint(st, &tmap_w, 0, (c_beg + g) * p.to, &bars.raw_full[s], pol_stream);   // one contiguous block
+          }
           ptx::tma_load_2d_ws(st + x_off, &tmap_x, kc * 2 * kMtBK, m * p.B, &bars.raw_full[s]);
         }
         if (q == 0 && lane == 0) MT_TRACE(0, g, 2);
@@ -482,6 +497,7 @@ k_mix_tc(MtParams p, const __grid_constant__ CUtensorMap tmap_w, const __grid_co
       if (++t == p.ntile) { t = 0; ++m; }
     }
   }
+  PDES_GRID_DEP_LAUNCH();                      // K3a may be scheduled as this CTA drains
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == kMtIssue0) {
@@ -635,7 +651,7 @@ int pdes_mix_tc_fwd(const float* X2, const float* Wp, float* O2, int B, int Cin,
   const size_t smem = (size_t)p.nst * stage_bytes + 1024;
   auto kfn = k_mix_tc;
   PDES_SET_SMEM(kfn, smem);
-  PDES_LAUNCH(kfn, dim3((unsigned)g.G), dim3(kMtThreads), smem, stream, p, tw, tx);
+  PDES_LAUNCH_PDL(kfn, dim3((unsigned)g.G), dim3(kMtThreads), smem, stream, p, tw, tx);
   return check_launch("pdes_mix_tc_fwd");
 #endif
 }
@@ -658,7 +674,7 @@ int pdes_inv_h_modes(const float* O2, int B, int C, int H, int m1, int m2, const
   auto kfn = k_inv_h2;
   if (smem > 48 * 1024) PDES_SET_SMEM(kfn, smem);
   PDES_MAX_CARVEOUT(kfn);
-  PDES_LAUNCH(kfn, dim3((unsigned)ceil_div(C, 32), (unsigned)m2, (unsigned)B), dim3((unsigned)(32 * nwarp)), smem, stream,
+  PDES_LAUNCH_PDL(kfn, dim3((unsigned)ceil_div(C, 32), (unsigned)m2, (unsigned)B), dim3((unsigned)(32 * nwarp)), smem, stream,
               reinterpret_cast<const float2*>(O2), B, C, H, m1, m2,
               reinterpret_cast<const float2*>(tables + table_layout(H, 2, m1, m2).twp), Z);
   return check_launch("pdes_inv_h_modes");
