@@ -229,10 +229,18 @@ int pdes_block_forward(const float* h, int C0, const float* vb, int C1, const fl
  * dwc [Cout][Cin] and dbias [Cout] (both may be NULL when there is no 1x1 conv). */
 size_t pdes_block_bwd_workspace_floats(int B, int C0, int C1, int Cout, int H, int W, int m1, int m2);
 int pdes_block_backward(const float* g_out, const float* pre, const float* h, int C0, const float* vb, int C1,
-                        const float* Xsave, const float* w1, const float* w2, const float* wc, const float* wpack,
-                        const float* tables, float* ws, float* g_pre, float* dh, float* gw1, float* gw2,
+                        const float* Xsave, const float* w1, const float* w2, const float* wspec, const float* wc,
+                        const float* wpack, const float* tables, float* ws, float* g_pre, float* dh, float* gw1, float* gw2,
                         float* dwc, float* dbias,
                         int B, int Cout, int H, int W, int m1, int m2, int act, void* stream);
+
+/* Adjoint of the per-mode channel mix w.r.t. the spectrum on tcgen05, from the FORWARD pack of pdes_mix_tc_pack (read as an
+ * MN-major operand: no second copy of the weights).  GO2 = mode-major gradient spectrum (pdes_dft_fwd2 on the output
+ * gradient with herm_scale = 1), O2 in the layout of pdes_mix_tc_fwd's output for the first C0 input channels.
+ * Replaces the autograd of compl_mul2d w.r.t. its input, proc_fno.py:253-255. */
+int pdes_mix_tc_dx_ok(int B, int Cin, int Cout, int C0, int m1, int m2);
+int pdes_mix_tc_dx(const float* GO2, const float* Wp, float* O2, int B, int Cin, int Cout, int C0, int m1, int m2,
+                   void* stream);
 
 #ifdef __cplusplus
 }

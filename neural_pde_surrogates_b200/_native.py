@@ -73,8 +73,10 @@ _PROTOTYPES = {
     "pdes_block_forward": (c_int, [_P, _I, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                                    _I, _I, _I, _I, _I, _I, _I, _P]),
     "pdes_block_bwd_workspace_floats": (c_size_t, [_I, _I, _I, _I, _I, _I, _I, _I]),
-    "pdes_block_backward": (c_int, [_P, _P, _P, _I, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
+    "pdes_block_backward": (c_int, [_P, _P, _P, _I, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                                     _I, _I, _I, _I, _I, _I, _I, _P]),
+    "pdes_mix_tc_dx_ok": (c_int, [_I, _I, _I, _I, _I, _I]),
+    "pdes_mix_tc_dx": (c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
 }
 
 EXPORTED_SYMBOLS = tuple(_PROTOTYPES)

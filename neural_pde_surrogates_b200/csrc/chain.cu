@@ -22,7 +22,7 @@ FwdWs fwd_ws(int B, int Cin, int Cout, int H, int W, int m1, int m2) {
   return w;
 }
 
-struct BwdWs { size_t GO, PX, Zg, WG, PK, total; int nsplit; };
+struct BwdWs { size_t GO, PX, Zg, WG, PK, GO2, O2g, total; int nsplit; };
 BwdWs bwd_ws(int B, int Cin, int C0, int Cout, int H, int W, int m1, int m2, bool has_conv) {
   BwdWs w;
   w.nsplit = pdes_mix_suggest_splits(B, Cout, C0, m1, m2);
@@ -34,7 +34,11 @@ BwdWs bwd_ws(int B, int Cin, int C0, int Cout, int H, int W, int m1, int m2, boo
   size_t wg = has_conv ? pdes_wgrad_workspace_floats(B, Cout, Cin, H * W) : 0;
   if (has_conv && pdes_wgrad_tc_workspace_floats(Cout, Cin) > wg) wg = pdes_wgrad_tc_workspace_floats(Cout, Cin);
   w.PK = w.WG + round4(wg);
-  w.total = w.PK + (has_conv ? round4(pdes_gemm_tc_pack_floats(Cout, C0)) : 0);
+  w.GO2 = w.PK + (has_conv ? round4(pdes_gemm_tc_pack_floats(Cout, C0)) : 0);
+  // dX on tcgen05 from the forward pack: mode-major gradient spectrum and its output in K2's O2 layout
+  const bool dx_tc = pdes_mix_tc_dx_ok(B, Cin, Cout, C0, m1, m2) != 0;
+  w.O2g = w.GO2 + (dx_tc ? round4(pdes_mix_tc_x2_floats(B, Cout, m1, m2)) : 0);
+  w.total = w.O2g + (dx_tc ? round4(pdes_mix_tc_o2_floats(B, C0, m1, m2)) : 0);
   return w;
 }
 
@@ -95,9 +99,9 @@ size_t pdes_block_bwd_workspace_floats(int B, int C0, int C1, int Cout, int H, i
 }
 
 int pdes_block_backward(const float* g_out, const float* pre, const float* h, int C0, const float* vb, int C1,
-                        const float* Xsave, const float* w1, const float* w2, const float* wc, const float* wpack,
-                        const float* tables, float* ws, float* g_pre, float* dh, float* gw1, float* gw2, float* dwc,
-                        float* dbias, int B, int Cout, int H, int W, int m1, int m2, int act, void* stream) {
+                        const float* Xsave, const float* w1, const float* w2, const float* wspec, const float* wc,
+                        const float* wpack, const float* tables, float* ws, float* g_pre, float* dh, float* gw1, float* gw2,
+                        float* dwc, float* dbias, int B, int Cout, int H, int W, int m1, int m2, int act, void* stream) {
   using namespace pdes;
   PDES_REQUIRE(g_out && h && Xsave && w1 && w2 && tables && ws && dh && gw1 && gw2, PDES_ERR_ARG,
                "pdes_block_backward: null pointer");
@@ -115,14 +119,26 @@ int pdes_block_backward(const float* g_out, const float* pre, const float* h, in
     if (int e = pdes_act_bwd(g_out, pre, g_pre, (size_t)B * Cout * H * W, act, stream)) return e;
     gp = g_pre;
   }
+  // dX of the channel mix on tcgen05 straight from the FORWARD pack (read as an MN-major operand): needs the pack and the
+  // mode-major copy of the gradient spectrum
+  const bool dx_tc = wspec != nullptr && pdes_mix_tc_dx_ok(B, Cin, Cout, C0, m1, m2) != 0;
   // GO = c_l/(HW) * DFT(g_pre)                     (adjoint of K3)
-  if (int e = pdes_dft_fwd(gp, Cout, nullptr, 0, B, H, W, m1, m2, tables, 1, GO, stream)) return e;
+  if (dx_tc) {
+    if (int e = pdes_dft_fwd2(gp, Cout, nullptr, 0, B, H, W, m1, m2, tables, 1, GO, ws + w.GO2, stream)) return e;
+  } else if (int e = pdes_dft_fwd(gp, Cout, nullptr, 0, B, H, W, m1, m2, tables, 1, GO, stream)) {
+    return e;
+  }
   // weight gradients in the parameter layout       (adjoint of K2 w.r.t. W)
   if (int e = pdes_mix_dw(Xsave, GO, gw1, gw2, B, Cin, Cout, H, m1, m2, stream)) return e;
-  // GX for the C0 channels that need a gradient    (adjoint of K2 w.r.t. X)
-  if (int e = pdes_mix_dx(GO, w1, w2, PX, w.nsplit, B, Cin, Cout, C0, H, m1, m2, stream)) return e;
+  // GX for the C0 channels that need a gradient    (adjoint of K2 w.r.t. X), then its H-axis inverse (unit weights)
+  if (dx_tc) {
+    if (int e = pdes_mix_tc_dx(ws + w.GO2, wspec, ws + w.O2g, B, Cin, Cout, C0, m1, m2, stream)) return e;
+    if (int e = pdes_inv_h_modes(ws + w.O2g, B, C0, H, m1, m2, tables, Zg, stream)) return e;
+  } else {
+    if (int e = pdes_mix_dx(GO, w1, w2, PX, w.nsplit, B, Cin, Cout, C0, H, m1, m2, stream)) return e;
+    if (int e = pdes_inv_h(PX, w.nsplit, B, C0, H, m1, m2, tables, Zg, stream)) return e;
+  }
   // dh = Re(pruned inverse of GX, unit weights) + wc^T g_pre      (adjoint of K1 fused with the 1x1 dX)
-  if (int e = pdes_inv_h(PX, w.nsplit, B, C0, H, m1, m2, tables, Zg, stream)) return e;
   if (has_conv && pdes_get_tensor_core_mode() && pdes_inv_w_gemm_tc_ok(C0, Cout, H, W, m2, gp, nullptr)) {
     const float* PK = wpack;                   // At[k = o][n = i] = wc[o][i], lda = Cin
     if (PK == nullptr) {

@@ -120,6 +120,14 @@ __host__ __device__ inline int kx_of(int k, int m1, int H) { return k < m1 ? k :
 // first-block rows overwritten by the second block when 2*m1 > H
 __host__ __device__ inline bool row_dead(int k, int m1, int H) { return k < m1 && k >= H - m1; }
 
+// geometry of the packed spectral weights Wp[m][tile][chunk][row][16 i][re|im] (spectral_mix_tc.cu, spectral_mix_adj_tc.cu)
+constexpr int kMtBK = 16;          // input channels per chunk
+constexpr int kMtMaxN = 64;        // padded 2B (two split accumulators x double buffering = 4 * N <= 256 TMEM columns)
+__host__ __device__ inline int mt_cinp(int Cin) { return (Cin + kMtBK - 1) / kMtBK * kMtBK; }
+__host__ __device__ inline int mt_npad(int B) { int n = (2 * B + 15) & ~15; return n < 16 ? 16 : n; }
+__host__ __device__ inline int mt_ntile(int Cout) { return (Cout + 127) / 128; }
+__host__ __device__ inline int mt_to(int Cout) { const int nt = mt_ntile(Cout); return (((Cout + nt - 1) / nt) + 7) & ~7; }
+
 __host__ __device__ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 

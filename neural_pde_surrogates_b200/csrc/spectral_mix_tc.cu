@@ -48,13 +48,6 @@
 
 namespace pdes {
 
-constexpr int kMtBK = 16;          // input channels per chunk
-constexpr int kMtMaxN = 64;        // padded 2B (two split accumulators x double buffering = 4 * N <= 256 TMEM columns)
-
-__host__ __device__ inline int mt_cinp(int Cin) { return (Cin + kMtBK - 1) / kMtBK * kMtBK; }
-__host__ __device__ inline int mt_npad(int B) { int n = (2 * B + 15) & ~15; return n < 16 ? 16 : n; }
-__host__ __device__ inline int mt_ntile(int Cout) { return (Cout + 127) / 128; }
-__host__ __device__ inline int mt_to(int Cout) { const int nt = mt_ntile(Cout); return (((Cout + nt - 1) / nt) + 7) & ~7; }
 
 namespace {
 

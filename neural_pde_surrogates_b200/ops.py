@@ -229,7 +229,7 @@ class FNOBlockFunction(torch.autograd.Function):
                     p(pre), B, Cout, H, W, m1, m2, act, _stream()))
             _counters["launches"] += 4 + (1 if (wc is not None and wpack_f is None) else 0)   # K1, K2, K3a, K3b (+ pack)
         if needs_grad:
-            ctx.save_for_backward(h, vb, w1c, w2c, wc, X, pre, wpack_b)
+            ctx.save_for_backward(h, vb, w1c, w2c, wc, X, pre, wpack_b, wspec)    # wspec: dX reads the forward pack too
             ctx.act = act
             ctx.has_res = res is not None
             ctx.has_bias = bias is not None
@@ -238,7 +238,7 @@ class FNOBlockFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         lib = _lib()
-        h, vb, w1, w2, wc, X, pre, wpack_b = ctx.saved_tensors
+        h, vb, w1, w2, wc, X, pre, wpack_b, wspec = ctx.saved_tensors
         if ctx.needs_input_grad[1]:
             raise NotImplementedError("gradient w.r.t. the broadcast conditioning channels is not implemented "
                                       "(they never require grad in the twophase configs, enc_proc_dec.py:126-137)")
@@ -264,7 +264,7 @@ class FNOBlockFunction(torch.autograd.Function):
             p = lambda t: None if t is None else t.data_ptr()
             with _Timed("block_backward"):
                 _native.check(lib, lib.pdes_block_backward(
-                    p(g), p(pre), p(h), C0, p(vb), C1, p(X), p(w1), p(w2), p(wc2), p(wpack_b), p(tab), p(ws), p(g_pre), p(dh),
+                    p(g), p(pre), p(h), C0, p(vb), C1, p(X), p(w1), p(w2), p(wspec), p(wc2), p(wpack_b), p(tab), p(ws), p(g_pre), p(dh),
                     p(gw1), p(gw2), p(dwc), p(dbias), B, Cout, H, W, m1, m2, act, _stream()))
             # act_bwd, K1(g), mix_dw, mix_dx, K3a, K3b, wgrad + its reduce
             _counters["launches"] += 5 + (1 if act != ACT_NONE else 0) + (2 if wc is not None else 0) + \

@@ -279,7 +279,7 @@ def run_block(be, shape, d, act=1, use_res=True, use_conv=True, spec_pack=False)
     dwc = be.empty((Cout, Cin))
     dbias = be.empty((Cout,))
     be.check(lib.pdes_block_backward(be.ptr(up["g"]), be.ptr(pre), be.ptr(up["h"]), C0, be.ptr(up["vb"]), C1,
-                                     be.ptr(X), be.ptr(up["w1"]), be.ptr(up["w2"]),
+                                     be.ptr(X), be.ptr(up["w1"]), be.ptr(up["w2"]), be.ptr(wspec),
                                      be.ptr(up["wc"]) if use_conv else None, None, be.ptr(tab), be.ptr(wsb),
                                      be.ptr(g_pre), be.ptr(dh), be.ptr(gw1), be.ptr(gw2),
                                      be.ptr(dwc) if use_conv else None, be.ptr(dbias) if use_conv else None,

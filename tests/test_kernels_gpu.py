@@ -219,7 +219,7 @@ def test_block_forward_backward_run_to_run_bitwise(be, B):
         gpre, dh = be.empty((B, Cout, H, W)), be.empty((B, C0, H, W))
         gw1, gw2 = be.empty(tuple(w1.shape), complex_=True), be.empty(tuple(w2.shape), complex_=True)
         dwc, dbias = be.empty((Cout, Cin)), be.empty((Cout,))
-        ck(lib.pdes_block_backward(p(gout), p(pre), p(h), C0, p(vb), C1, p(X), p(w1), p(w2), p(wc), None, p(tab), p(wsb),
+        ck(lib.pdes_block_backward(p(gout), p(pre), p(h), C0, p(vb), C1, p(X), p(w1), p(w2), p(wsp), p(wc), None, p(tab), p(wsb),
                                    p(gpre), p(dh), p(gw1), p(gw2), p(dwc), p(dbias), B, Cout, H, W, m1, m2, 1, st))
         return dict(X=torch.view_as_real(X), out=out, pre=pre, gpre=gpre, dh=dh, gw1=torch.view_as_real(gw1),
                     gw2=torch.view_as_real(gw2), dwc=dwc, dbias=dbias)
@@ -243,3 +243,37 @@ def test_dft_fwd_tensor_core_opt_in(be, herm, monkeypatch):
         kc.check_dft_fwd(be, shape, herm)
     monkeypatch.delenv("PDES_K1_TC")
     kc.check_dft_fwd(be, (1, 3, 1, 4, 96, 64, 10, 10), herm)
+
+
+@pytest.mark.parametrize("shape", [FULL_SHAPES[0], FULL_SHAPES[2], (3, 128, 1, 96, 32, 32, 6, 5), (16, 64, 0, 160, 16, 16, 4, 4)])
+def test_mix_dx_tensor_core(be, shape):
+    """pdes_mix_tc_dx (the adjoint of the channel mix read from the FORWARD pack as an MN-major operand) against the float64
+    oracle, through its own entry point: GO2 from pdes_dft_fwd2-style mode-major data, output in K2's O2 layout."""
+    import numpy as np
+    from oracle import spectral_oracle as so
+    lib, p, ck = be.lib, be.ptr, be.check
+    B, C0, C1, Cout, H, W, m1, m2 = shape
+    Cin = C0 + C1
+    if not lib.pdes_mix_tc_dx_ok(B, Cin, Cout, C0, m1, m2):
+        pytest.skip("shape outside pdes_mix_tc_dx")
+    rng = np.random.default_rng(7)
+    w1, w2 = kc._weights(rng, Cin, Cout, m1, m2)
+    GO = (rng.standard_normal((B, Cout, 2 * m1, m2)) + 1j * rng.standard_normal((B, Cout, 2 * m1, m2))).astype(np.complex64)
+    CoutP = (Cout + 15) // 16 * 16
+    go2 = np.full((2 * m1 * m2, B, CoutP), np.nan + 1j * np.nan, dtype=np.complex64)       # pad columns must never be used
+    go2[:, :, :Cout] = GO.transpose(2, 3, 0, 1).reshape(2 * m1 * m2, B, Cout)
+    dw1, dw2, dgo = be.upload(w1), be.upload(w2), be.upload(go2)
+    wsp = be.empty((lib.pdes_mix_tc_pack_floats(Cin, Cout, m1, m2),))
+    ck(lib.pdes_mix_tc_pack(p(dw1), p(dw2), p(wsp), Cin, Cout, H, m1, m2, be.stream))
+    first = None
+    for rep in range(3):                                              # repeated: the ring / mode hand-over must not depend on timing
+        o2 = be.empty((2, 2 * m1 * m2, B, C0), complex_=True)
+        ck(lib.pdes_mix_tc_dx(p(dgo), p(wsp), p(o2), B, Cin, Cout, C0, m1, m2, be.stream))
+        got = be.download(o2)
+        assert np.all(got[1] == 0)
+        first = got if first is None else first
+        assert np.array_equal(got.view(np.float32), first.view(np.float32), equal_nan=True)
+    gx = first[0].reshape(2 * m1, m2, B, C0).transpose(2, 3, 0, 1)
+    ref = so.mode_mix_dx(GO.astype(np.complex128), w1, w2, H)[:, :C0]
+    err = so.rel_l2(gx, ref)
+    assert err < kc.TOL, f"mix_tc_dx {shape}: rel L2 {err:.3e}"

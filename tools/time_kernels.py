@@ -92,6 +92,8 @@ def main():
                                16 * Cin * Cout * MM + 8 * B * Cin * 2 * MM + 8 * B * Cout * 2 * MM),
             "K3a_inv_h_modes": (lambda: ck(lib.pdes_inv_h_modes(p(O2), B, Cout, H, m1, m2, p(tab), p(Z), st)),
                                 8 * B * Cout * 2 * MM + 4 * B * H * 2 * m2 * Cout),
+            "K2_dx_tcgen05": (lambda: ck(lib.pdes_mix_tc_dx(p(X2), p(wsp), p(O2), B, Cin, Cout, C0, m1, m2, st)),
+                              16 * Cin * Cout * MM + 8 * B * Cout * 2 * MM + 8 * B * C0 * 2 * MM),
             "spectral_weight_pack": (lambda: ck(lib.pdes_mix_tc_pack(p(w1), p(w2), p(wsp), Cin, Cout, H, m1, m2, st)),
                                      32 * Cin * Cout * MM),
             "block_forward_tc_cached_packs": (lambda: ck(lib.pdes_block_forward(p(h), C0, p(vb), C1, p(w1), p(w2), p(wsp), p(wc), p(pack1), p(bias),
@@ -125,7 +127,7 @@ def main():
                       4 * B * (Cin + Cout) * HW),
             "wgrad_tcgen05": (lambda: ck(lib.pdes_wgrad_tc(p(g), p(h), C0, p(vb), C1, p(dwc), p(dbias), p(wgtc), B, Cout, HW, st)),
                               4 * B * (Cin + Cout) * HW),
-            "block_backward": (lambda: ck(lib.pdes_block_backward(p(g), p(pre), p(h), C0, p(vb), C1, p(X), p(w1), p(w2), p(wc), None,
+            "block_backward": (lambda: ck(lib.pdes_block_backward(p(g), p(pre), p(h), C0, p(vb), C1, p(X), p(w1), p(w2), p(wsp), p(wc), None,
                                                                   p(tab), p(wsb), p(gpre), p(dh), p(gw1), p(gw2), p(dwc), p(dbias),
                                                                   B, Cout, H, W, m1, m2, 1, st)),
                                4 * B * (3 * Cout + 2 * Cin + C0) * HW + 32 * Cin * Cout * MM),
