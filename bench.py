@@ -361,7 +361,7 @@ def leg_train(hx: Harness, args, wl: Workload):
 def leg_rollout(hx: Harness, args, wl: Workload, tr, model, pde):
     """Config #4: 50-step autoregressive rollout, trajectories sharded over the ranks, NO collective in the timed
     region (the max over ranks of the per-rank time is taken afterwards)."""
-    from neural_pde_surrogates_b200 import dp
+    from neural_pde_surrogates_b200 import dp, ops
     dev = hx.dev
     n_total = args.rollout_batch * hx.world
     mine = dp.shard_trajectories(n_total, hx.rank, hx.world)
@@ -376,13 +376,23 @@ def leg_rollout(hx: Harness, args, wl: Workload, tr, model, pde):
               use_bc=False, divide_by_t=False)
     res, ok, finite, err = {}, 1.0, True, ""
     modes = ("eager", "graph", "graph_k") if hx.graphs else ("eager",)
+    extra_chain = {}
     model.eval()
     try:
         with torch.no_grad():
             for mode in modes:
                 gk = dict(graph=(mode != "eager"), steps_per_graph=(args.rollout_steps_per_graph if mode == "graph_k" else 1))
                 tr.simulate(u, cond, pos, **gk, **dict(kw, t_res=wl.tw * (1 + max(2, gk["steps_per_graph"]))))   # warm-up / capture
+                if mode == "eager":                                        # the no-grad chain (no pre-activation store), in situ
+                    ops.collect_timings()
+                    ops.enable_timing(True)
                 res[mode] = hx.timed(lambda: tr.simulate(u, cond, pos, **gk, **kw), 1)
+                if mode == "eager":
+                    ops.enable_timing(False)
+                    ch = ops.collect_timings()["block_forward"]
+                    if ch:
+                        extra_chain["nograd_us"] = statistics.mean(ch) * 1e3
+                        extra_chain["launches"] = len(ch)
             preds = tr.simulate(u, cond, pos, graph=hx.graphs, **dict(kw, t_res=wl.tw * 3))
             finite = bool(torch.isfinite(preds[-1]).all())
     except Exception as exc:                                              # noqa: BLE001  (no collective was pending)
@@ -405,6 +415,8 @@ def leg_rollout(hx: Harness, args, wl: Workload, tr, model, pde):
             out["steps_per_graph"] = args.rollout_steps_per_graph
     else:
         out["error"] = err or "failed on another rank"
+    if extra_chain:
+        out["chain_nograd"] = extra_chain
     return out
 
 
@@ -580,9 +592,15 @@ def run_legs(hx: Harness, args, wl: Workload = WL):
                              "achieved": ach, "peak": peak, "unit": "GB/s", "frac": (ach / peak) if ach else None,
                              "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                              "alg_bytes_per_launch": wl.block_bytes(B), "us_per_launch": fwd_us,
-                             "launches_timed": len(chain["block_forward"]), "block_backward_us": bwd_us},
+                             "launches_timed": len(chain["block_forward"]), "block_backward_us": bwd_us,
+                             "note": "frac is the chain inside the timed TRAINING steps (it also stores the pre-activation, "
+                                     "75 MB not counted in the algorithmic bytes); nograd_* is the same chain in the rollout leg"},
                 "cpu_baseline": cpu}
         line.update(extra)
+        ng = (extra.get("rollout") or {}).get("chain_nograd")
+        if ng and args.rollout_batch == B:
+            line["roofline"]["nograd_us_per_launch"] = ng["nograd_us"]
+            line["roofline"]["nograd_frac"] = wl.block_bytes(B) / (ng["nograd_us"] * 1e-6) / 1e9 / peak
     return line
 
 

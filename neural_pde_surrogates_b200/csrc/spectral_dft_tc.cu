@@ -51,7 +51,7 @@ struct D1Params {
   const float* lscale;      // [m2] Hermitian weights (backward of irfft2) or null
   const float2* twh;        // [H] (cos, sin)(2 pi j / H)
   const float2* tw2;        // [m2][W + 1] (cos, sin)(2 pi l w / W)
-  int B, C0, C1, CinP, H, m1, m2, nimg, dbg;
+  int B, C0, C1, CinP, H, m1, m2, nimg;
 };
 
 #ifdef PDES_K1_TRACE
@@ -399,7 +399,6 @@ int dft_fwd_tc_try(const float* x0, int C0, const float* x1, int C1, int B, int 
   p.twh = reinterpret_cast<const float2*>(tables + t.twh);
   p.tw2 = reinterpret_cast<const float2*>(tables + t.tw2);
   p.B = B; p.C0 = C0; p.C1 = C1; p.CinP = CinP; p.H = H; p.m1 = m1; p.m2 = m2; p.nimg = B * (C0 + C1);
-  p.dbg = 0;
   const size_t smem = (size_t)kD1Stages * 4 * H * 128 + (size_t)2 * 2 * kD1A2Bytes + (size_t)2 * (H + kD1W) * kD1N * 4 + 1024;
   if (smem > 227 * 1024) return -1;
   if (g_d1_sms == 0) {
