@@ -874,15 +874,18 @@ k_wgrad_tc(WgtParams p, const __grid_constant__ CUtensorMap tmap_g, const __grid
       raw_empty[kWgtRaw], done_bar;
   __shared__ uint32_t tmem_slot;
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // (warp index as a warp-uniform value: the MMA and TMA roles run warp-converged with one elected lane issuing, see
+  // DESIGN.md 3.1-2; as `if (lane == 0)` roles every tcgen05.mma / TMA issue sat in a waterfall loop)
+  const int tid = threadIdx.x, warp = ptx::uniform_warp_idx(), lane = tid & 31;
   const int cpi = p.HW / kTcBK;                                   // chunks per image
   const int c_beg = blockIdx.x * p.per_cta;
   const int c_end = (c_beg + p.per_cta < p.total_chunks) ? (c_beg + p.per_cta) : p.total_chunks;
   const int nch = c_end - c_beg;
 
   if (tid == 0) {
-    for (int i = 0; i < kWgtStages; ++i) { ptx::mbar_init(&full_bar[i], 256); ptx::mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < kWgtRaw; ++i) { ptx::mbar_init(&raw_full[i], 1); ptx::mbar_init(&raw_empty[i], 256); }
+    // one arrival per convert WARP (after __syncwarp), not per thread: 256 arrivals on one barrier word serialise
+    for (int i = 0; i < kWgtStages; ++i) { ptx::mbar_init(&full_bar[i], 8); ptx::mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < kWgtRaw; ++i) { ptx::mbar_init(&raw_full[i], 1); ptx::mbar_init(&raw_empty[i], 8); }
     ptx::mbar_init(&done_bar, 1);
     ptx::fence_mbar_init();
   }
@@ -925,9 +928,14 @@ k_wgrad_tc(WgtParams p, const __grid_constant__ CUtensorMap tmap_g, const __grid
         *reinterpret_cast<float4*>(dst) = hi;
         *reinterpret_cast<float4*>(dst + (row < p.mrows ? a_blk : b_blk)) = lo;
       }
-      ptx::mbar_arrive(&raw_empty[r]);
+      // (both arrivals come after the st.shared of the converted data: the raw slot is released only once its values
+      // have been consumed)
       ptx::fence_proxy_async();
-      ptx::mbar_arrive(&full_bar[s]);
+      __syncwarp();
+      if (lane == 0) {
+        ptx::mbar_arrive(&raw_empty[r]);
+        ptx::mbar_arrive(&full_bar[s]);
+      }
     }
     // ================================================================== epilogue: one partial per CTA
     if (nch > 0) {
@@ -956,8 +964,8 @@ k_wgrad_tc(WgtParams p, const __grid_constant__ CUtensorMap tmap_g, const __grid
     }
     ptx::tc_fence_before();
   } else if (warp == 8) {
-    if (lane == 0 && nch > 0) {
-      // ================================================================ MMA issue
+    if (nch > 0) {
+      // ================================================================ MMA issue (warp-converged, one elected lane issues)
       const uint32_t idesc = ptx::idesc_tf32(128, p.npadN);
       const uint32_t row1 = (uint32_t)((p.mrows - 128) / 8) * 128;           // byte offset of the second 128-row tile
       const uint32_t sbase = ptx::smem_u32(base);
@@ -978,28 +986,29 @@ k_wgrad_tc(WgtParams p, const __grid_constant__ CUtensorMap tmap_g, const __grid
             const uint64_t ka = ds + (uint64_t)((ks * 2 * lbo_a + (t ? row1 : 0u)) >> 4);
             const uint32_t dcol = tmem_base + (uint32_t)t * 256;
             const uint32_t accf = (c | ks) != 0 ? 1u : 0u;
-            ptx::mma_tf32(dcol, a_lo0 + ka, b_hi0 + kb, idesc, accf);
-            ptx::mma_tf32(dcol, a_hi0 + ka, b_lo0 + kb, idesc, 1u);
-            ptx::mma_tf32(dcol, a_hi0 + ka, b_hi0 + kb, idesc, 1u);
+            ptx::mma_tf32_ws(dcol, a_lo0 + ka, b_hi0 + kb, idesc, accf);
+            ptx::mma_tf32_ws(dcol, a_hi0 + ka, b_lo0 + kb, idesc, 1u);
+            ptx::mma_tf32_ws(dcol, a_hi0 + ka, b_hi0 + kb, idesc, 1u);
           }
         }
-        ptx::tc_commit(&empty_bar[s]);
+        ptx::tc_commit_ws(&empty_bar[s]);
       }
-      ptx::tc_commit(&done_bar);
+      ptx::tc_commit_ws(&done_bar);
     }
-  } else if (lane == 0) {
-    // ================================================================== TMA issue
+  } else {
+    // ================================================================== TMA issue (warp-converged)
+    int b = c_beg / cpi, pc = c_beg - b * cpi;                    // counters instead of a division per chunk
     for (int c = 0; c < nch; ++c) {
       const uint32_t r = c % kWgtRaw;
       if (c >= kWgtRaw) ptx::mbar_wait(&raw_empty[r], ((c / kWgtRaw) - 1) & 1);
-      const int gc = c_beg + c;
-      const int b = gc / cpi, px = (gc - b * cpi) * kTcBK;
+      const int px = pc * kTcBK;
       float* dst = raw + (size_t)r * raw_f;
-      ptx::mbar_arrive_expect_tx(&raw_full[r], (uint32_t)(p.M + p.K) * kTcBK * 4);
-      ptx::tma_load_2d(dst, &tmap_g, px, b * p.M, &raw_full[r]);
-      ptx::tma_load_2d(dst + off_x0, &tmap_x0, px, b * p.x0_ld + p.x0_off, &raw_full[r]);
+      ptx::mbar_arrive_expect_tx_ws(&raw_full[r], (uint32_t)(p.M + p.K) * kTcBK * 4);
+      ptx::tma_load_2d_ws(dst, &tmap_g, px, b * p.M, &raw_full[r]);
+      ptx::tma_load_2d_ws(dst + off_x0, &tmap_x0, px, b * p.x0_ld + p.x0_off, &raw_full[r]);
       for (int k = 0; k < p.C1; ++k)
-        ptx::bulk_g2s(dst + off_x0 + (p.C0 + k) * kTcBK, p.x1 + ((size_t)b * p.C1 + k) * p.HW + px, kTcBK * 4, &raw_full[r]);
+        ptx::bulk_g2s_ws(dst + off_x0 + (p.C0 + k) * kTcBK, p.x1 + ((size_t)b * p.C1 + k) * p.HW + px, kTcBK * 4, &raw_full[r]);
+      if (++pc == cpi) { pc = 0; ++b; }
     }
   }
   __syncthreads();
