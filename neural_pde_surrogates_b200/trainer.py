@@ -45,8 +45,16 @@ class DataCreator:
             data = dp[:, :, s - tw:s] if mode != "labels" else None
             labels = dp[:, :, s:s + tw] if mode != "data" else None
         else:
-            data = torch.stack([dp[i, :, s - tw:s] for i, s in enumerate(steps)]) if mode != "labels" else None
-            labels = torch.stack([dp[i, :, s:s + tw] for i, s in enumerate(steps)]) if mode != "data" else None
+            # Device-side window gather: ONE index op per tensor instead of a Python loop of per-sample
+            # slices + cat (data_creator.py:60-74).  rows[i, j] = steps[i] - tw + j for the data, steps[i] + j for the labels.
+            st = torch.as_tensor(steps, device=dp.device, dtype=torch.long)
+            off = torch.arange(tw, device=dp.device, dtype=torch.long)
+            bi = torch.arange(n, device=dp.device, dtype=torch.long)[:, None]
+
+            def window(start):                                   # dp [n, C, T, H, W] -> [n, C, tw, H, W]
+                return dp[bi, :, (start[:, None] + off)[:, :]].transpose(1, 2).contiguous()
+            data = window(st - tw) if mode != "labels" else None
+            labels = window(st) if mode != "data" else None
         if mode == "data":
             return data
         if mode == "labels":

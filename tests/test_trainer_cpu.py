@@ -63,3 +63,22 @@ def test_epoch_loop_schedule_and_checkpoint(tmp_path):
     sd = torch.load(tmp_path / "ckpt_final.pt")
     assert list(sd) == list(before) and (tmp_path / "ckpt_unrolled.pt").exists()
     assert any(not torch.equal(sd[k], before[k]) for k in sd)
+
+
+def test_create_data_device_side_gather_matches_per_sample_slices():
+    """DataCreator.create_data with per-sample window starts is one index op per tensor; it must equal the reference's
+    Python loop of slices + cat (src/common/data_creator.py:48-78) for data, labels and both modes, equal and ragged starts."""
+    from neural_pde_surrogates_b200.trainer import DataCreator
+    torch.manual_seed(3)
+    tw = 5
+    dc = DataCreator(None, time_window=tw, t_resolution=40)
+    dp = torch.randn(6, 2, 40, 4, 3)
+    for steps in ([5, 9, 30, 35], [7, 7, 7], [35, 5, 20, 11, 6, 30]):
+        ref_d = torch.stack([dp[i, :, s - tw:s] for i, s in enumerate(steps)])
+        ref_l = torch.stack([dp[i, :, s:s + tw] for i, s in enumerate(steps)])
+        d, l = dc.create_data(dp, steps)
+        assert torch.equal(d, ref_d) and torch.equal(l, ref_l)
+        assert torch.equal(dc.create_data(dp, steps, mode="data"), ref_d)
+        assert torch.equal(dc.create_data(dp, steps, mode="labels"), ref_l)
+    with pytest.raises(AssertionError):
+        dc.create_data(dp, [3, 10])                                    # window would start before t = 0
