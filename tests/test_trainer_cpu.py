@@ -1,5 +1,6 @@
 """CPU suite: push-forward train_step (unroll 0/1/2), test_step and the window slicer against the unmodified
 reference trainer's outputs (golden) -- host-side logic, kernels replaced by the torch port."""
+import pytest
 import torch
 
 from oracle.torch_port import cpu_port
